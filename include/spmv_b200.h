@@ -1,0 +1,215 @@
+/*
+ * spmv_b200.h -- C ABI of the B200 (sm_100a) CSR SpMV library, libspmvb200.so.
+ *
+ * This is the drop-in boundary for the reference's SpMV hot path.  Each typed entry
+ * point below is what one instantiation of a reference kind
+ *
+ *     template <index_t, offset_t, mat_value_t, vec_x_value_t, vec_y_value_t>
+ *     void SpMV_xxx(index_t n_rows, index_t n_cols, offset_t nnz,
+ *                   const offset_t *Ap, const index_t *Aj, const mat_value_t *Ax,
+ *                   const vec_x_value_t *x, vec_y_value_t *y);
+ *
+ * (reference/include/spmv/cusp/cusp.cuh:227-230, LightSpMV.cuh:379,
+ *  merge_based/merge_based.cuh:22, cusparse.cuh:37-40; dispatched from
+ *  reference/include/spmv.h:29-48) binds to.  include/spmv.h in this repository holds
+ * the templates that forward to these symbols, so `SpMV(kind_str, ...)` keeps the
+ * reference signature.
+ *
+ * Contract:
+ *   - all five arrays are DEVICE pointers owned by the caller; Ap, Aj, Ax, x are
+ *     read-only; y (n_rows entries) is fully overwritten: y = A*x (alpha = 1, beta = 0),
+ *     empty rows give 0; n_rows == 0 or n_cols == 0 is a no-op;
+ *   - index type is int32; offsets are int32 (o32) or int64 (o64); values, x and y share
+ *     one type, float (f32) or double (f64);
+ *   - Ap, Aj, Ax must be 16-byte aligned (cudaMalloc gives 256); checked, not assumed:
+ *     SPMVB200_ERR_ALIGNMENT otherwise;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = the legacy
+ *     default stream) and the call returns without synchronising;
+ *   - the return value is 0 or an SPMVB200_ERR_* code; nothing is printed, nothing
+ *     aborts: include/spmv.h turns a non-zero status into the reference's
+ *     print-and-exit behaviour (reference/include/common.cuh:13-23, spmv.h:46-47);
+ *   - one host thread per (device, stream) at a time; scratch (tile coordinates, carries,
+ *     row counter, row statistics) is cached inside the library per (device, stream);
+ *   - there is NO CPU fallback: without a CUDA device every call returns
+ *     SPMVB200_ERR_CUDA.
+ */
+#ifndef SPMV_B200_H_
+#define SPMV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPMVB200_API __attribute__((visibility("default")))
+
+typedef void *spmvb200_stream_t; /* cudaStream_t */
+
+enum {
+    SPMVB200_OK = 0,
+    SPMVB200_ERR_INVALID = 1,   /* negative size, NULL pointer with non-zero size */
+    SPMVB200_ERR_ALIGNMENT = 2, /* Ap / Aj / Ax not 16-byte aligned */
+    SPMVB200_ERR_CUDA = 3,      /* a CUDA runtime call failed; see spmvb200_last_cuda_error */
+    SPMVB200_ERR_UNSUPPORTED = 4,
+    SPMVB200_ERR_CUSPARSE = 5
+};
+
+/* kinds: the new SPMV_KINDS labels */
+enum {
+    SPMVB200_KIND_MERGE = 0,  /* "merge":  merge-path tiles + partition + carry fixup     */
+    SPMVB200_KIND_VECTOR = 1, /* "vector": CSR-vector, sub-warp per row, shuffle reduce   */
+    SPMVB200_KIND_LIGHT = 2,  /* "light":  LightSpMV-style dynamic row hand-out (atomics) */
+    SPMVB200_KIND_AUTO = 3,   /* "auto":   host selector from cached row statistics       */
+    SPMVB200_KIND_CUSPARSE = 4 /* "cusparse": cusparseSpMV baseline, setup hoisted         */
+};
+
+SPMVB200_API const char *spmvb200_status_string(int status);
+SPMVB200_API const char *spmvb200_last_cuda_error(void);
+SPMVB200_API const char *spmvb200_version(void);
+
+/* ---- the hot path: one symbol per (kind, offset type, value type) ------------------ */
+#define SPMVB200_DECLARE(KIND, OTAG, OFF_T, VTAG, VAL_T)                                   \
+    SPMVB200_API int spmvb200_##KIND##_i32_##OTAG##_##VTAG(                                \
+        int32_t n_rows, int32_t n_cols, OFF_T nnz, const OFF_T *Ap, const int32_t *Aj,    \
+        const VAL_T *Ax, const VAL_T *x, VAL_T *y, spmvb200_stream_t stream);
+#define SPMVB200_DECLARE_KIND(KIND)                       \
+    SPMVB200_DECLARE(KIND, o32, int32_t, f32, float)      \
+    SPMVB200_DECLARE(KIND, o32, int32_t, f64, double)     \
+    SPMVB200_DECLARE(KIND, o64, int64_t, f32, float)      \
+    SPMVB200_DECLARE(KIND, o64, int64_t, f64, double)
+
+/* replaces SpMV_merge_based / SpMV_merge_based_generalized / SpMV_cub_merge_based
+ * (reference/include/spmv/merge_based/merge_based.cuh:22, merge_genl/merge_genl.cuh:41,
+ *  cub_merge.cuh:20) */
+SPMVB200_DECLARE_KIND(merge)
+/* replaces SpMV_cusp_origin / SpMV_cusp_warp_reduce / SpMV_cusp_warp_read_reduce
+ * (reference/include/spmv/cusp/cusp.cuh:227, cusp_warp_reduce.cuh:138,
+ *  cusp_warp_read_reduce.cuh:144) */
+SPMVB200_DECLARE_KIND(vector)
+/* replaces SpMV_light_vector / SpMV_light_warp (reference/include/spmv/LightSpMV.cuh:379,399) */
+SPMVB200_DECLARE_KIND(light)
+/* new: per-matrix selector (BASELINE.json north_star "host-side selector") */
+SPMVB200_DECLARE_KIND(auto)
+/* replaces SpMV_cusparse (reference/include/spmv/cusparse.cuh:37-88); comparison baseline */
+SPMVB200_DECLARE_KIND(cusparse)
+
+/* Untyped form of the same call, for bindings that carry the types as data
+ * (ctypes, the multi-GPU driver).  offset_bits in {32, 64}, value_bits in {32, 64}.
+ * alpha_dev: optional DEVICE pointer to one value-typed scalar; y = (*alpha_dev) * A*x.
+ * NULL means 1.  (merge_based/agent_spmv_orig.cuh:425-433 carries alpha the same way.)
+ * y_peers / n_peers: optional array (HOST memory) of extra DEVICE pointers that receive the
+ * same y stores (peer-mapped buffers of other GPUs; the fused SpMV + all-gather of the
+ * row-sharded power iteration).  Each is indexed like y.  Supported by merge/vector/light. */
+typedef struct {
+    int32_t kind;
+    int32_t offset_bits;
+    int32_t value_bits;
+    int32_t n_peers;
+    int64_t n_rows;
+    int64_t n_cols;
+    int64_t nnz;
+    const void *Ap;
+    const int32_t *Aj;
+    const void *Ax;
+    const void *x;
+    void *y;
+    const void *alpha_dev;
+    void *const *y_peers;
+    spmvb200_stream_t stream;
+} spmvb200_args_t;
+SPMVB200_API int spmvb200_spmv(const spmvb200_args_t *args);
+
+/* ---- merge-path partition, exposed so parity tests can demand bit-exact coordinates --- */
+/* Row coordinate of the merge path on each diagonal min(t * tile_items, n_rows + nnz),
+ * t = 0 .. n_coords-1, written to the DEVICE array coords_x (int32).  The nonzero
+ * coordinate is diagonal - coords_x[t].
+ * Replaces DeviceSpmvSearchKernel (reference/include/spmv/merge_based/dispatch_spmv_orig.cuh:109-148)
+ * and SearchMergePath (merge_based/thread_search.cuh:16-49). */
+SPMVB200_API int spmvb200_merge_path_partition_o32(int32_t n_rows, int32_t nnz, const int32_t *Ap,
+                                                   int64_t tile_items, int64_t n_coords,
+                                                   int32_t *coords_x, spmvb200_stream_t stream);
+SPMVB200_API int spmvb200_merge_path_partition_o64(int32_t n_rows, int64_t nnz, const int64_t *Ap,
+                                                   int64_t tile_items, int64_t n_coords,
+                                                   int32_t *coords_x, spmvb200_stream_t stream);
+/* tile size (merge items per thread block) the merge kernel uses for this type pair */
+SPMVB200_API int64_t spmvb200_merge_tile_items(int offset_bits, int value_bits);
+
+/* nnz-balanced row split for `parts` shards: row_bounds (HOST, parts+1
+ * int64) from the merge path on diagonals floor(g*(n_rows+nnz)/parts).  Synchronises. */
+SPMVB200_API int spmvb200_row_split_o32(int32_t n_rows, int32_t nnz, const int32_t *Ap, int parts,
+                                        int64_t *row_bounds, spmvb200_stream_t stream);
+SPMVB200_API int spmvb200_row_split_o64(int32_t n_rows, int64_t nnz, const int64_t *Ap, int parts,
+                                        int64_t *row_bounds, spmvb200_stream_t stream);
+
+/* ---- row statistics + selector --------------------------------------------------------- */
+typedef struct {
+    int64_t n_rows;
+    int64_t nnz;
+    int64_t max_row_len;
+    int64_t empty_rows;
+    double mean_row_len;
+    double std_row_len;
+    int32_t chosen_kind;  /* what "auto" runs for this matrix */
+    int32_t chosen_width; /* lanes per row for vector / light */
+} spmvb200_row_stats_t;
+/* One pass over Ap on the device, result cached keyed on (Ap, n_rows, nnz).  Synchronises
+ * the stream the first time a matrix is seen. */
+SPMVB200_API int spmvb200_row_stats(int offset_bits, int64_t n_rows, int64_t nnz, const void *Ap,
+                                    spmvb200_row_stats_t *out, spmvb200_stream_t stream);
+
+/* ---- tunables (benchmarking / ablation); names in DESIGN.md --------------------------- */
+SPMVB200_API int spmvb200_set_option(const char *name, int64_t value);
+SPMVB200_API int64_t spmvb200_get_option(const char *name);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+SPMVB200_API int64_t spmvb200_launch_count(void);
+/* drop cached scratch / statistics (all devices) */
+SPMVB200_API void spmvb200_release_cache(void);
+
+/* ---- host-buffer convenience: the end-to-end call --------------------------------------
+ * A CSR matrix uploaded once (as reference/main.cu:55-69 does), then y = A*x with x and y
+ * in HOST memory: H2D copy of x, kernel, D2H copy of y, stream synchronised on return. */
+typedef struct spmvb200_matrix spmvb200_matrix_t;
+SPMVB200_API int spmvb200_matrix_create(int offset_bits, int value_bits, int64_t n_rows,
+                                        int64_t n_cols, int64_t nnz, const void *Ap_host,
+                                        const int32_t *Aj_host, const void *Ax_host,
+                                        spmvb200_matrix_t **out);
+SPMVB200_API int spmvb200_matrix_spmv_host(spmvb200_matrix_t *m, int kind, const void *x_host,
+                                           void *y_host);
+SPMVB200_API void spmvb200_matrix_destroy(spmvb200_matrix_t *m);
+
+/* ---- device-side data layer: synthetic generators and COO -> CSR ------------------------
+ * Counter-based (splitmix64) so the host restatement in oracle/generators.py matches bit
+ * for bit.  All pointers are DEVICE pointers. */
+SPMVB200_API int spmvb200_gen_uniform_pm1(int value_bits, uint64_t seed, uint32_t stream_id,
+                                          uint64_t first, int64_t count, void *out,
+                                          spmvb200_stream_t stream);
+SPMVB200_API int spmvb200_gen_lap2d(int offset_bits, int value_bits, int32_t grid_n, void *Ap,
+                                    int32_t *Aj, void *Ax, spmvb200_stream_t stream);
+SPMVB200_API int spmvb200_gen_uniform_rows(int offset_bits, int value_bits, int32_t n_rows,
+                                           int32_t n_cols, int32_t row_len, uint64_t seed,
+                                           void *Ap, int32_t *Aj, void *Ax,
+                                           spmvb200_stream_t stream);
+SPMVB200_API int spmvb200_gen_rmat_edges(int32_t scale, uint64_t seed, uint64_t first_edge,
+                                         int64_t count, int32_t *rows, int32_t *cols,
+                                         spmvb200_stream_t stream);
+/* Stable COO -> CSR (input order kept within a row, duplicates kept), 64-bit safe.
+ * Replaces ToCsr (reference/include/load.hpp:420-474).  rows/cols are clobbered (used as
+ * sort buffers); vals may be NULL (pattern only: Aj and Ap written).  Allocates its own
+ * temporaries and synchronises. */
+SPMVB200_API int spmvb200_coo_to_csr(int offset_bits, int value_bits, int32_t n_rows, int64_t nnz,
+                                     int32_t *rows, int32_t *cols, const void *vals, void *Ap,
+                                     int32_t *Aj, void *Ax, spmvb200_stream_t stream);
+
+/* ---- peer mapping for the fused SpMV + all-gather (one process per GPU) ---------------- */
+#define SPMVB200_IPC_HANDLE_BYTES 64
+SPMVB200_API int spmvb200_ipc_export(void *dev_ptr, unsigned char handle[SPMVB200_IPC_HANDLE_BYTES]);
+SPMVB200_API int spmvb200_ipc_open(const unsigned char handle[SPMVB200_IPC_HANDLE_BYTES],
+                                   void **dev_ptr);
+SPMVB200_API int spmvb200_ipc_close(void *dev_ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPMV_B200_H_ */

@@ -1,0 +1,369 @@
+// api.cu -- the extern "C" surface declared in include/spmv_b200.h.
+//
+// Argument checking, type dispatch and the host-buffer convenience object live here; the
+// kernels are in merge.cu / vector.cu / light.cu, the selector and cuSPARSE baseline in
+// select.cu, the data layer in gen.cu.
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace spmvb200 {
+int64_t merge_tile_items();
+void stats_cache_clear();
+void cusparse_plan_clear();
+template <typename ValT>
+int gen_uniform_pm1(uint64_t, uint32_t, uint64_t, int64_t, ValT *, cudaStream_t);
+template <typename OffT, typename ValT>
+int gen_lap2d(int32_t, OffT *, int32_t *, ValT *, cudaStream_t);
+template <typename OffT, typename ValT>
+int gen_uniform_rows(int32_t, int32_t, int32_t, uint64_t, OffT *, int32_t *, ValT *, cudaStream_t);
+int gen_rmat_edges(int32_t, uint64_t, uint64_t, int64_t, int32_t *, int32_t *, cudaStream_t);
+template <typename OffT, typename ValT>
+int coo_to_csr(int32_t, int64_t, int32_t *, int32_t *, const ValT *, OffT *, int32_t *, ValT *,
+               cudaStream_t);
+
+namespace {
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <typename OffT, typename ValT>
+int run(int kind, int64_t n_rows, int64_t n_cols, int64_t nnz, const void *Ap, const int32_t *Aj,
+        const void *Ax, const void *x, void *y, const void *alpha_dev, void *const *y_peers,
+        int n_peers, cudaStream_t stream) {
+    if (n_rows < 0 || n_cols < 0 || nnz < 0) return SPMVB200_ERR_INVALID;
+    if (n_rows > 0x7fffffffLL || n_cols > 0x7fffffffLL) return SPMVB200_ERR_INVALID;
+    if (sizeof(OffT) == 4 && nnz > 0x7fffffffLL) return SPMVB200_ERR_INVALID;
+    // the reference's no-op case (merge_based/dispatch_spmv_orig.cuh:564-570)
+    if (n_rows == 0 || n_cols == 0) return SPMVB200_OK;
+    if (!Ap || !y || (nnz > 0 && (!Aj || !Ax || !x))) return SPMVB200_ERR_INVALID;
+    if (!aligned16(Ap) || !aligned16(Aj) || !aligned16(Ax)) return SPMVB200_ERR_ALIGNMENT;
+    if (n_peers < 0 || n_peers > kMaxPeers || (n_peers > 0 && !y_peers)) return SPMVB200_ERR_INVALID;
+
+    SpmvProblem<OffT, ValT> p;
+    p.n_rows = (int32_t)n_rows;
+    p.n_cols = (int32_t)n_cols;
+    p.nnz = (OffT)nnz;
+    p.Ap = static_cast<const OffT *>(Ap);
+    p.Aj = Aj;
+    p.Ax = static_cast<const ValT *>(Ax);
+    p.x = static_cast<const ValT *>(x);
+    p.y = static_cast<ValT *>(y);
+    p.alpha_dev = static_cast<const ValT *>(alpha_dev);
+    p.peers.n = n_peers;
+    for (int i = 0; i < kMaxPeers; ++i) p.peers.ptr[i] = i < n_peers ? y_peers[i] : nullptr;
+    p.stream = stream;
+
+    switch (kind) {
+        case SPMVB200_KIND_MERGE: return launch_merge<OffT, ValT>(p);
+        case SPMVB200_KIND_VECTOR: return launch_vector<OffT, ValT>(p, 0);
+        case SPMVB200_KIND_LIGHT: return launch_light<OffT, ValT>(p, 0);
+        case SPMVB200_KIND_AUTO: return launch_auto<OffT, ValT>(p);
+        case SPMVB200_KIND_CUSPARSE: return launch_cusparse<OffT, ValT>(p);
+        default: return SPMVB200_ERR_INVALID;
+    }
+}
+
+int run_untyped(const spmvb200_args_t *a) {
+    if (!a) return SPMVB200_ERR_INVALID;
+    cudaStream_t s = static_cast<cudaStream_t>(a->stream);
+#define GO(O, V)                                                                              \
+    return run<O, V>(a->kind, a->n_rows, a->n_cols, a->nnz, a->Ap, a->Aj, a->Ax, a->x, a->y,  \
+                     a->alpha_dev, a->y_peers, a->n_peers, s)
+    if (a->offset_bits == 32 && a->value_bits == 32) GO(int32_t, float);
+    if (a->offset_bits == 32 && a->value_bits == 64) GO(int32_t, double);
+    if (a->offset_bits == 64 && a->value_bits == 32) GO(int64_t, float);
+    if (a->offset_bits == 64 && a->value_bits == 64) GO(int64_t, double);
+#undef GO
+    return SPMVB200_ERR_UNSUPPORTED;
+}
+
+}  // namespace
+}  // namespace spmvb200
+
+using namespace spmvb200;
+
+extern "C" {
+
+// ---- typed hot-path symbols ---------------------------------------------------------------
+#define SPMVB200_DEFINE(KIND, KIND_ENUM, OTAG, OFF_T, VTAG, VAL_T)                              \
+    int spmvb200_##KIND##_i32_##OTAG##_##VTAG(int32_t n_rows, int32_t n_cols, OFF_T nnz,        \
+                                              const OFF_T *Ap, const int32_t *Aj,               \
+                                              const VAL_T *Ax, const VAL_T *x, VAL_T *y,        \
+                                              spmvb200_stream_t stream) {                       \
+        return run<OFF_T, VAL_T>(KIND_ENUM, n_rows, n_cols, (int64_t)nnz, Ap, Aj, Ax, x, y,     \
+                                 nullptr, nullptr, 0, static_cast<cudaStream_t>(stream));       \
+    }
+#define SPMVB200_DEFINE_KIND(KIND, KIND_ENUM)                       \
+    SPMVB200_DEFINE(KIND, KIND_ENUM, o32, int32_t, f32, float)      \
+    SPMVB200_DEFINE(KIND, KIND_ENUM, o32, int32_t, f64, double)     \
+    SPMVB200_DEFINE(KIND, KIND_ENUM, o64, int64_t, f32, float)      \
+    SPMVB200_DEFINE(KIND, KIND_ENUM, o64, int64_t, f64, double)
+SPMVB200_DEFINE_KIND(merge, SPMVB200_KIND_MERGE)
+SPMVB200_DEFINE_KIND(vector, SPMVB200_KIND_VECTOR)
+SPMVB200_DEFINE_KIND(light, SPMVB200_KIND_LIGHT)
+SPMVB200_DEFINE_KIND(auto, SPMVB200_KIND_AUTO)
+SPMVB200_DEFINE_KIND(cusparse, SPMVB200_KIND_CUSPARSE)
+
+int spmvb200_spmv(const spmvb200_args_t *args) { return run_untyped(args); }
+
+// ---- partition / row split -----------------------------------------------------------------
+int spmvb200_merge_path_partition_o32(int32_t n_rows, int32_t nnz, const int32_t *Ap,
+                                      int64_t tile_items, int64_t n_coords, int32_t *coords_x,
+                                      spmvb200_stream_t stream) {
+    if (n_rows < 0 || nnz < 0 || tile_items <= 0 || n_coords < 0 || !Ap || !coords_x)
+        return SPMVB200_ERR_INVALID;
+    return launch_partition<int32_t>(n_rows, nnz, Ap, tile_items, n_coords, coords_x,
+                                     static_cast<cudaStream_t>(stream));
+}
+int spmvb200_merge_path_partition_o64(int32_t n_rows, int64_t nnz, const int64_t *Ap,
+                                      int64_t tile_items, int64_t n_coords, int32_t *coords_x,
+                                      spmvb200_stream_t stream) {
+    if (n_rows < 0 || nnz < 0 || tile_items <= 0 || n_coords < 0 || !Ap || !coords_x)
+        return SPMVB200_ERR_INVALID;
+    return launch_partition<int64_t>(n_rows, nnz, Ap, tile_items, n_coords, coords_x,
+                                     static_cast<cudaStream_t>(stream));
+}
+int64_t spmvb200_merge_tile_items(int, int) { return merge_tile_items(); }
+
+}  // extern "C"
+
+namespace {
+// diagonals floor(g*total/parts) are not an arithmetic progression in general, so the split
+// reuses the partition kernel once per boundary with tile_items = that diagonal, n_coords = 2
+// (coordinate 1 is the one wanted).  parts is tiny.
+template <typename OffT>
+int row_split_impl(int32_t n_rows, OffT nnz, const OffT *Ap, int parts, int64_t *row_bounds,
+                   cudaStream_t stream) {
+    if (parts < 1 || !row_bounds || n_rows < 0 || nnz < 0 || (!Ap && n_rows > 0))
+        return SPMVB200_ERR_INVALID;
+    const int64_t total = (int64_t)n_rows + (int64_t)nnz;
+    void *dbuf = nullptr;
+    SPMV_TRY(scratch_get(stream, SCRATCH_MISC, (size_t)(parts + 1) * 2 * sizeof(int32_t), &dbuf));
+    int32_t *d = static_cast<int32_t *>(dbuf);
+    row_bounds[0] = 0;
+    for (int g = 1; g < parts; ++g) {
+        const int64_t diag = (int64_t)(((__int128)g * (__int128)total) / parts);
+        if (diag == 0) {
+            SPMV_CUDA_TRY(cudaMemsetAsync(d + 2 * g, 0, 2 * sizeof(int32_t), stream));
+        } else {
+            SPMV_TRY(launch_partition<OffT>(n_rows, nnz, Ap, diag, 2, d + 2 * g, stream));
+        }
+    }
+    std::vector<int32_t> h((size_t)(parts + 1) * 2, 0);
+    if (parts > 1)
+        SPMV_CUDA_TRY(cudaMemcpyAsync(h.data(), d, h.size() * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                      stream));
+    SPMV_CUDA_TRY(cudaStreamSynchronize(stream));
+    for (int g = 1; g < parts; ++g) row_bounds[g] = h[2 * g + 1];
+    row_bounds[parts] = n_rows;
+    return SPMVB200_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int spmvb200_row_split_o32(int32_t n_rows, int32_t nnz, const int32_t *Ap, int parts,
+                           int64_t *row_bounds, spmvb200_stream_t stream) {
+    return row_split_impl<int32_t>(n_rows, nnz, Ap, parts, row_bounds, static_cast<cudaStream_t>(stream));
+}
+int spmvb200_row_split_o64(int32_t n_rows, int64_t nnz, const int64_t *Ap, int parts,
+                           int64_t *row_bounds, spmvb200_stream_t stream) {
+    return row_split_impl<int64_t>(n_rows, nnz, Ap, parts, row_bounds, static_cast<cudaStream_t>(stream));
+}
+
+// ---- statistics ----------------------------------------------------------------------------
+int spmvb200_row_stats(int offset_bits, int64_t n_rows, int64_t nnz, const void *Ap,
+                       spmvb200_row_stats_t *out, spmvb200_stream_t stream) {
+    if (!out || n_rows < 0 || nnz < 0 || (!Ap && n_rows > 0)) return SPMVB200_ERR_INVALID;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (offset_bits == 32) return row_stats<int32_t>(n_rows, nnz, static_cast<const int32_t *>(Ap), out, s);
+    if (offset_bits == 64) return row_stats<int64_t>(n_rows, nnz, static_cast<const int64_t *>(Ap), out, s);
+    return SPMVB200_ERR_UNSUPPORTED;
+}
+
+void spmvb200_release_cache(void) {
+    stats_cache_clear();
+    cusparse_plan_clear();
+    scratch_release_all();
+}
+
+}  // extern "C"
+
+// ---- host-buffer matrix object -------------------------------------------------------------
+struct spmvb200_matrix {
+    int offset_bits, value_bits;
+    int64_t n_rows, n_cols, nnz;
+    void *Ap = nullptr, *Ax = nullptr, *x = nullptr, *y = nullptr;
+    int32_t *Aj = nullptr;
+    cudaStream_t stream = nullptr;
+};
+
+extern "C" {
+
+int spmvb200_matrix_create(int offset_bits, int value_bits, int64_t n_rows, int64_t n_cols,
+                           int64_t nnz, const void *Ap_host, const int32_t *Aj_host,
+                           const void *Ax_host, spmvb200_matrix_t **out) {
+    if (!out || n_rows < 0 || n_cols < 0 || nnz < 0) return SPMVB200_ERR_INVALID;
+    if ((offset_bits != 32 && offset_bits != 64) || (value_bits != 32 && value_bits != 64))
+        return SPMVB200_ERR_UNSUPPORTED;
+    if (!Ap_host || (nnz > 0 && (!Aj_host || !Ax_host))) return SPMVB200_ERR_INVALID;
+    spmvb200_matrix *m = new (std::nothrow) spmvb200_matrix;
+    if (!m) return SPMVB200_ERR_INVALID;
+    m->offset_bits = offset_bits;
+    m->value_bits = value_bits;
+    m->n_rows = n_rows;
+    m->n_cols = n_cols;
+    m->nnz = nnz;
+    const size_t ob = offset_bits / 8, vb = value_bits / 8;
+    auto fail = [&](cudaError_t e, const char *what) {
+        record_cuda_error(e, what, __FILE__, __LINE__);
+        spmvb200_matrix_destroy(m);
+        return SPMVB200_ERR_CUDA;
+    };
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+    if ((e = cudaMalloc(&m->Ap, (size_t)(n_rows + 1) * ob)) != cudaSuccess) return fail(e, "cudaMalloc Ap");
+    if ((e = cudaMalloc((void **)&m->Aj, (size_t)(nnz ? nnz : 1) * 4)) != cudaSuccess) return fail(e, "cudaMalloc Aj");
+    if ((e = cudaMalloc(&m->Ax, (size_t)(nnz ? nnz : 1) * vb)) != cudaSuccess) return fail(e, "cudaMalloc Ax");
+    if ((e = cudaMalloc(&m->x, (size_t)(n_cols ? n_cols : 1) * vb)) != cudaSuccess) return fail(e, "cudaMalloc x");
+    if ((e = cudaMalloc(&m->y, (size_t)(n_rows ? n_rows : 1) * vb)) != cudaSuccess) return fail(e, "cudaMalloc y");
+    if ((e = cudaMemcpyAsync(m->Ap, Ap_host, (size_t)(n_rows + 1) * ob, cudaMemcpyHostToDevice, m->stream)) != cudaSuccess) return fail(e, "H2D Ap");
+    if (nnz > 0) {
+        if ((e = cudaMemcpyAsync(m->Aj, Aj_host, (size_t)nnz * 4, cudaMemcpyHostToDevice, m->stream)) != cudaSuccess) return fail(e, "H2D Aj");
+        if ((e = cudaMemcpyAsync(m->Ax, Ax_host, (size_t)nnz * vb, cudaMemcpyHostToDevice, m->stream)) != cudaSuccess) return fail(e, "H2D Ax");
+    }
+    if ((e = cudaStreamSynchronize(m->stream)) != cudaSuccess) return fail(e, "sync");
+    *out = m;
+    return SPMVB200_OK;
+}
+
+int spmvb200_matrix_spmv_host(spmvb200_matrix_t *m, int kind, const void *x_host, void *y_host) {
+    if (!m || (!x_host && m->n_cols > 0) || (!y_host && m->n_rows > 0)) return SPMVB200_ERR_INVALID;
+    const size_t vb = m->value_bits / 8;
+    if (m->n_cols > 0)
+        SPMV_CUDA_TRY(cudaMemcpyAsync(m->x, x_host, (size_t)m->n_cols * vb, cudaMemcpyHostToDevice, m->stream));
+    spmvb200_args_t a;
+    std::memset(&a, 0, sizeof(a));
+    a.kind = kind;
+    a.offset_bits = m->offset_bits;
+    a.value_bits = m->value_bits;
+    a.n_rows = m->n_rows;
+    a.n_cols = m->n_cols;
+    a.nnz = m->nnz;
+    a.Ap = m->Ap;
+    a.Aj = m->Aj;
+    a.Ax = m->Ax;
+    a.x = m->x;
+    a.y = m->y;
+    a.stream = m->stream;
+    SPMV_TRY(spmvb200_spmv(&a));
+    if (m->n_rows > 0) {
+        if (m->n_cols == 0) SPMV_CUDA_TRY(cudaMemsetAsync(m->y, 0, (size_t)m->n_rows * vb, m->stream));
+        SPMV_CUDA_TRY(cudaMemcpyAsync(y_host, m->y, (size_t)m->n_rows * vb, cudaMemcpyDeviceToHost, m->stream));
+    }
+    SPMV_CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return SPMVB200_OK;
+}
+
+void spmvb200_matrix_destroy(spmvb200_matrix_t *m) {
+    if (!m) return;
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    if (m->Ap) cudaFree(m->Ap);
+    if (m->Aj) cudaFree(m->Aj);
+    if (m->Ax) cudaFree(m->Ax);
+    if (m->x) cudaFree(m->x);
+    if (m->y) cudaFree(m->y);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+// ---- generators / data layer ---------------------------------------------------------------
+int spmvb200_gen_uniform_pm1(int value_bits, uint64_t seed, uint32_t stream_id, uint64_t first,
+                             int64_t count, void *out, spmvb200_stream_t stream) {
+    if (count < 0 || (!out && count > 0)) return SPMVB200_ERR_INVALID;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (value_bits == 32) return gen_uniform_pm1<float>(seed, stream_id, first, count, static_cast<float *>(out), s);
+    if (value_bits == 64) return gen_uniform_pm1<double>(seed, stream_id, first, count, static_cast<double *>(out), s);
+    return SPMVB200_ERR_UNSUPPORTED;
+}
+
+#define DISPATCH_OV(FN, ...)                                                                   \
+    do {                                                                                       \
+        if (offset_bits == 32 && value_bits == 32) return FN<int32_t, float>(__VA_ARGS__);     \
+        if (offset_bits == 32 && value_bits == 64) return FN<int32_t, double>(__VA_ARGS__);    \
+        if (offset_bits == 64 && value_bits == 32) return FN<int64_t, float>(__VA_ARGS__);     \
+        if (offset_bits == 64 && value_bits == 64) return FN<int64_t, double>(__VA_ARGS__);    \
+        return SPMVB200_ERR_UNSUPPORTED;                                                       \
+    } while (0)
+
+}  // extern "C"
+
+namespace {
+template <typename OffT, typename ValT>
+int lap2d_v(int32_t n, void *Ap, int32_t *Aj, void *Ax, cudaStream_t s) {
+    return gen_lap2d<OffT, ValT>(n, static_cast<OffT *>(Ap), Aj, static_cast<ValT *>(Ax), s);
+}
+template <typename OffT, typename ValT>
+int uniform_rows_v(int32_t n_rows, int32_t n_cols, int32_t K, uint64_t seed, void *Ap, int32_t *Aj,
+                   void *Ax, cudaStream_t s) {
+    return gen_uniform_rows<OffT, ValT>(n_rows, n_cols, K, seed, static_cast<OffT *>(Ap), Aj,
+                                        static_cast<ValT *>(Ax), s);
+}
+template <typename OffT, typename ValT>
+int coo_to_csr_v(int32_t n_rows, int64_t nnz, int32_t *rows, int32_t *cols, const void *vals,
+                 void *Ap, int32_t *Aj, void *Ax, cudaStream_t s) {
+    return coo_to_csr<OffT, ValT>(n_rows, nnz, rows, cols, static_cast<const ValT *>(vals),
+                                  static_cast<OffT *>(Ap), Aj, static_cast<ValT *>(Ax), s);
+}
+}  // namespace
+
+extern "C" {
+
+int spmvb200_gen_lap2d(int offset_bits, int value_bits, int32_t grid_n, void *Ap, int32_t *Aj,
+                       void *Ax, spmvb200_stream_t stream) {
+    if (!Ap || !Aj || !Ax) return SPMVB200_ERR_INVALID;
+    DISPATCH_OV(lap2d_v, grid_n, Ap, Aj, Ax, static_cast<cudaStream_t>(stream));
+}
+int spmvb200_gen_uniform_rows(int offset_bits, int value_bits, int32_t n_rows, int32_t n_cols,
+                              int32_t row_len, uint64_t seed, void *Ap, int32_t *Aj, void *Ax,
+                              spmvb200_stream_t stream) {
+    if (!Ap || !Aj || !Ax) return SPMVB200_ERR_INVALID;
+    DISPATCH_OV(uniform_rows_v, n_rows, n_cols, row_len, seed, Ap, Aj, Ax, static_cast<cudaStream_t>(stream));
+}
+int spmvb200_gen_rmat_edges(int32_t scale, uint64_t seed, uint64_t first_edge, int64_t count,
+                            int32_t *rows, int32_t *cols, spmvb200_stream_t stream) {
+    if (count < 0 || (count > 0 && (!rows || !cols))) return SPMVB200_ERR_INVALID;
+    return gen_rmat_edges(scale, seed, first_edge, count, rows, cols, static_cast<cudaStream_t>(stream));
+}
+int spmvb200_coo_to_csr(int offset_bits, int value_bits, int32_t n_rows, int64_t nnz, int32_t *rows,
+                        int32_t *cols, const void *vals, void *Ap, int32_t *Aj, void *Ax,
+                        spmvb200_stream_t stream) {
+    if (!Ap || (nnz > 0 && (!rows || !cols || !Aj)) || (vals && !Ax)) return SPMVB200_ERR_INVALID;
+    DISPATCH_OV(coo_to_csr_v, n_rows, nnz, rows, cols, vals, Ap, Aj, Ax, static_cast<cudaStream_t>(stream));
+}
+
+// ---- peer mapping --------------------------------------------------------------------------
+int spmvb200_ipc_export(void *dev_ptr, unsigned char handle[SPMVB200_IPC_HANDLE_BYTES]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == SPMVB200_IPC_HANDLE_BYTES, "handle size");
+    if (!dev_ptr || !handle) return SPMVB200_ERR_INVALID;
+    cudaIpcMemHandle_t h;
+    SPMV_CUDA_TRY(cudaIpcGetMemHandle(&h, dev_ptr));
+    std::memcpy(handle, &h, sizeof(h));
+    return SPMVB200_OK;
+}
+int spmvb200_ipc_open(const unsigned char handle[SPMVB200_IPC_HANDLE_BYTES], void **dev_ptr) {
+    if (!handle || !dev_ptr) return SPMVB200_ERR_INVALID;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    SPMV_CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return SPMVB200_OK;
+}
+int spmvb200_ipc_close(void *dev_ptr) {
+    if (!dev_ptr) return SPMVB200_ERR_INVALID;
+    SPMV_CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+    return SPMVB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,228 @@
+// common.cuh -- shared host/device plumbing of libspmvb200 (sm_100a only).
+//
+// Replaces reference/include/common.cuh:1-23 (checkCudaErr -> abort) with status codes,
+// and holds the PTX wrappers the three kernels share: mbarrier + cp.async.bulk (TMA 1-D
+// bulk copies, SASS UBLKCP), L2 cache-policy loads, and warp reductions.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/spmv_b200.h"
+
+namespace spmvb200 {
+
+// ------------------------------------------------------------------ host: status + errors
+void record_cuda_error(cudaError_t e, const char *what, const char *file, int line);
+void count_launch(int n = 1);
+
+#define SPMV_CUDA_TRY(expr)                                                    \
+    do {                                                                       \
+        cudaError_t _e = (expr);                                               \
+        if (_e != cudaSuccess) {                                               \
+            ::spmvb200::record_cuda_error(_e, #expr, __FILE__, __LINE__);      \
+            return SPMVB200_ERR_CUDA;                                          \
+        }                                                                      \
+    } while (0)
+
+#define SPMV_TRY(expr)                          \
+    do {                                        \
+        int _s = (expr);                        \
+        if (_s != SPMVB200_OK) return _s;       \
+    } while (0)
+
+// after a kernel launch
+#define SPMV_LAUNCH_CHECK()                     \
+    do {                                        \
+        ::spmvb200::count_launch();             \
+        SPMV_CUDA_TRY(cudaGetLastError());      \
+    } while (0)
+
+struct DeviceInfo {
+    int device = -1;
+    int sm_count = 0;
+    int max_threads_per_sm = 0;
+    size_t l2_bytes = 0;
+    size_t persisting_l2_max = 0;
+    size_t access_window_max = 0;
+    size_t smem_optin = 0;
+};
+int current_device_info(const DeviceInfo **out);
+
+// Per-(device, stream) scratch that survives across calls, grown on demand.
+// Slots keep independent buffers so a kernel can hold several at once.
+enum ScratchSlot { SCRATCH_COORDS = 0, SCRATCH_CARRY_ROW, SCRATCH_CARRY_VAL, SCRATCH_COUNTER,
+                   SCRATCH_STATS, SCRATCH_MISC, SCRATCH_NUM_SLOTS };
+int scratch_get(cudaStream_t stream, ScratchSlot slot, size_t bytes, void **out);
+void scratch_release_all();
+
+int64_t option_get(const char *name, int64_t fallback);
+
+// Extra destinations of every y store (peer GPUs' replicas of the next x).
+constexpr int kMaxPeers = 8;
+struct PeerOut {
+    void *ptr[kMaxPeers];
+    int n;
+};
+
+template <typename OffT, typename ValT>
+struct SpmvProblem {
+    int32_t n_rows;
+    int32_t n_cols;
+    OffT nnz;
+    const OffT *Ap;
+    const int32_t *Aj;
+    const ValT *Ax;
+    const ValT *x;
+    ValT *y;
+    const ValT *alpha_dev;  // device scalar or nullptr (= 1)
+    PeerOut peers;
+    cudaStream_t stream;
+};
+
+// launchers (one translation unit each)
+template <typename OffT, typename ValT> int launch_merge(const SpmvProblem<OffT, ValT> &p);
+template <typename OffT, typename ValT> int launch_vector(const SpmvProblem<OffT, ValT> &p, int width);
+template <typename OffT, typename ValT> int launch_light(const SpmvProblem<OffT, ValT> &p, int width);
+template <typename OffT, typename ValT> int launch_cusparse(const SpmvProblem<OffT, ValT> &p);
+template <typename OffT, typename ValT> int launch_auto(const SpmvProblem<OffT, ValT> &p);
+template <typename OffT>
+int launch_partition(int32_t n_rows, OffT nnz, const OffT *Ap, int64_t tile_items, int64_t n_coords,
+                     int32_t *coords_x, cudaStream_t stream);
+template <typename OffT>
+int row_stats(int64_t n_rows, int64_t nnz, const OffT *Ap, spmvb200_row_stats_t *out,
+              cudaStream_t stream);
+int pick_width_from_mean(double mean_row_len);
+
+// Launch attribute helper: optional L2 access-policy window over x (option "l2_window").
+struct LaunchCfg {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attrs[2];
+};
+void make_launch_cfg(LaunchCfg &lc, dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                     const void *x, size_t x_bytes);
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------ device: PTX wrappers
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+// make the init visible to the async (TMA) proxy
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
+// L2 eviction policies (createpolicy): streams are read once, x is re-read.
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
+// TMA 1-D bulk copy global -> shared, completion on an mbarrier.  dst, src 16-byte
+// aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes,
+                                         uint64_t *bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
+// gather of x with an L2 policy (evict_last keeps x resident against the Aj/Ax stream)
+__device__ __forceinline__ float ldg_hint(const float *p, uint64_t policy) {
+    float v;
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ double ldg_hint(const double *p, uint64_t policy) {
+    double v;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy));
+    return v;
+}
+
+// 128-bit streaming loads (read once: no L1 allocation, L2 evict-first policy)
+__device__ __forceinline__ int4 ldg_stream_int4(const int32_t *p, uint64_t policy) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(policy));
+    return r;
+}
+__device__ __forceinline__ float4 ldg_stream_val4(const float *p, uint64_t policy) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p), "l"(policy));
+    return r;
+}
+struct double4_t {
+    double x, y, z, w;
+};
+__device__ __forceinline__ double4_t ldg_stream_val4(const double *p, uint64_t policy) {
+    double4_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
+                 : "=d"(r.x), "=d"(r.y)
+                 : "l"(p), "l"(policy));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
+                 : "=d"(r.z), "=d"(r.w)
+                 : "l"(p + 2), "l"(policy));
+    return r;
+}
+
+template <typename ValT> struct Val4;
+template <> struct Val4<float> { using type = float4; };
+template <> struct Val4<double> { using type = double4_t; };
+
+// sum over the T lanes of a sub-warp (T a power of two <= 32); every lane gets the total
+template <int T, typename ValT>
+__device__ __forceinline__ ValT subwarp_sum(ValT v) {
+#pragma unroll
+    for (int s = T / 2; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s, 32);
+    return v;
+}
+
+// y store fanned out to the peer replicas
+template <typename ValT>
+__device__ __forceinline__ void store_y(ValT *y, const PeerOut &peers, int64_t row, ValT v) {
+    y[row] = v;
+#pragma unroll
+    for (int i = 0; i < kMaxPeers; ++i)
+        if (i < peers.n) static_cast<ValT *>(peers.ptr[i])[row] = v;
+}
+#endif  // __CUDACC__
+
+}  // namespace spmvb200

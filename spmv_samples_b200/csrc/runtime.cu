@@ -1,0 +1,194 @@
+// runtime.cu -- host-side runtime of libspmvb200: error slots, device properties, the
+// per-(device, stream) scratch cache, tunables, launch counter, launch attributes.
+//
+// Replaces the reference's per-call cudaMalloc/cudaFree of temporaries
+// (reference/include/spmv/cusparse.cuh:72,88; cub_merge.cuh:43,54; LightSpMV.cuh:274,314;
+// merge_based/merge_based.cuh:34,46 -- the last one leaks) with buffers that are allocated
+// once and grown on demand, so the steady-state call makes no allocation and no sync.
+#include <atomic>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "common.cuh"
+
+namespace spmvb200 {
+
+namespace {
+std::mutex g_mu;
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+std::map<int, DeviceInfo> g_devs;
+
+struct ScratchBuf {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+struct ScratchSet {
+    ScratchBuf slot[SCRATCH_NUM_SLOTS];
+};
+std::map<std::pair<int, cudaStream_t>, ScratchSet> g_scratch;
+
+std::map<std::string, int64_t> &options() {
+    static std::map<std::string, int64_t> o = {
+        {"l2_window", 0},        // 1: attach an L2 access-policy persistence window over x
+        {"vector_width", 0},     // 0: from row statistics; else force lanes per row (1..32)
+        {"light_width", 0},      // same for the dynamic-row kernel
+        {"light_rows_per_claim", 0},  // 0: automatic
+        {"auto_kind", -1},       // -1: selector decides; else force a SPMVB200_KIND_*
+    };
+    return o;
+}
+}  // namespace
+
+void record_cuda_error(cudaError_t e, const char *what, const char *file, int line) {
+    std::snprintf(g_err, sizeof(g_err), "%s:%d: %s -> %s (%s)", file, line, what,
+                  cudaGetErrorName(e), cudaGetErrorString(e));
+    (void)cudaGetLastError();  // clear the sticky-less error so the next call starts clean
+}
+
+const char *last_error() { return g_err; }
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+int current_device_info(const DeviceInfo **out) {
+    int dev = -1;
+    SPMV_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_devs.find(dev);
+    if (it == g_devs.end()) {
+        cudaDeviceProp prop;
+        SPMV_CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+        DeviceInfo di;
+        di.device = dev;
+        di.sm_count = prop.multiProcessorCount;
+        di.max_threads_per_sm = prop.maxThreadsPerMultiProcessor;
+        di.l2_bytes = (size_t)prop.l2CacheSize;
+        di.persisting_l2_max = (size_t)prop.persistingL2CacheMaxSize;
+        di.access_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+        di.smem_optin = (size_t)prop.sharedMemPerBlockOptin;
+        it = g_devs.emplace(dev, di).first;
+    }
+    *out = &it->second;
+    return SPMVB200_OK;
+}
+
+int scratch_get(cudaStream_t stream, ScratchSlot slot, size_t bytes, void **out) {
+    int dev = -1;
+    SPMV_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_mu);
+    ScratchBuf &b = g_scratch[{dev, stream}].slot[slot];
+    if (bytes < 256) bytes = 256;
+    if (b.bytes < bytes) {
+        // grow geometrically; the old buffer may still be in use by queued kernels on this
+        // stream, so free it stream-ordered
+        size_t want = bytes + bytes / 4;
+        void *np = nullptr;
+        SPMV_CUDA_TRY(cudaMalloc(&np, want));
+        if (b.ptr) {
+            SPMV_CUDA_TRY(cudaStreamSynchronize(stream));
+            SPMV_CUDA_TRY(cudaFree(b.ptr));
+        }
+        b.ptr = np;
+        b.bytes = want;
+    }
+    *out = b.ptr;
+    return SPMVB200_OK;
+}
+
+void scratch_release_all() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int cur = -1;
+    cudaGetDevice(&cur);
+    for (auto &kv : g_scratch) {
+        cudaSetDevice(kv.first.first);
+        cudaDeviceSynchronize();
+        for (auto &b : kv.second.slot)
+            if (b.ptr) cudaFree(b.ptr);
+    }
+    g_scratch.clear();
+    if (cur >= 0) cudaSetDevice(cur);
+}
+
+int64_t option_get(const char *name, int64_t fallback) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = options().find(name);
+    return it == options().end() ? fallback : it->second;
+}
+int option_set(const char *name, int64_t v) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = options().find(name);
+    if (it == options().end()) return SPMVB200_ERR_INVALID;
+    it->second = v;
+    return SPMVB200_OK;
+}
+
+void make_launch_cfg(LaunchCfg &lc, dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                     const void *x, size_t x_bytes) {
+    std::memset(&lc, 0, sizeof(lc));
+    lc.cfg.gridDim = grid;
+    lc.cfg.blockDim = block;
+    lc.cfg.dynamicSmemBytes = smem;
+    lc.cfg.stream = stream;
+    lc.cfg.attrs = lc.attrs;
+    lc.cfg.numAttrs = 0;
+    if (x && x_bytes && option_get("l2_window", 0) > 0) {
+        const DeviceInfo *di = nullptr;
+        if (current_device_info(&di) == SPMVB200_OK && di->access_window_max > 0 &&
+            di->persisting_l2_max > 0) {
+            static std::map<int, bool> limit_set;
+            {
+                std::lock_guard<std::mutex> lk(g_mu);
+                if (!limit_set[di->device]) {
+                    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, di->persisting_l2_max);
+                    limit_set[di->device] = true;
+                }
+            }
+            size_t win = x_bytes < di->access_window_max ? x_bytes : di->access_window_max;
+            float ratio = win <= di->persisting_l2_max
+                              ? 1.0f
+                              : (float)((double)di->persisting_l2_max / (double)win);
+            cudaLaunchAttribute &a = lc.attrs[lc.cfg.numAttrs++];
+            a.id = cudaLaunchAttributeAccessPolicyWindow;
+            a.val.accessPolicyWindow.base_ptr = const_cast<void *>(x);
+            a.val.accessPolicyWindow.num_bytes = win;
+            a.val.accessPolicyWindow.hitRatio = ratio;
+            a.val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            a.val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        }
+    }
+}
+
+}  // namespace spmvb200
+
+// ------------------------------------------------------------------------ C ABI (misc)
+namespace spmvb200 {
+const char *last_error();
+int64_t launch_count();
+int option_set(const char *name, int64_t v);
+}  // namespace spmvb200
+
+extern "C" {
+
+const char *spmvb200_status_string(int status) {
+    switch (status) {
+        case SPMVB200_OK: return "ok";
+        case SPMVB200_ERR_INVALID: return "invalid argument";
+        case SPMVB200_ERR_ALIGNMENT: return "Ap/Aj/Ax must be 16-byte aligned";
+        case SPMVB200_ERR_CUDA: return "CUDA runtime error";
+        case SPMVB200_ERR_UNSUPPORTED: return "unsupported configuration";
+        case SPMVB200_ERR_CUSPARSE: return "cuSPARSE error";
+        default: return "unknown status";
+    }
+}
+const char *spmvb200_last_cuda_error(void) { return spmvb200::last_error(); }
+const char *spmvb200_version(void) { return "spmvb200 0.1 (sm_100a)"; }
+int spmvb200_set_option(const char *name, int64_t value) { return spmvb200::option_set(name, value); }
+int64_t spmvb200_get_option(const char *name) { return spmvb200::option_get(name, -1); }
+int64_t spmvb200_launch_count(void) { return spmvb200::launch_count(); }
+
+}  // extern "C"

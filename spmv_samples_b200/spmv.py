@@ -1,0 +1,191 @@
+"""Host-side mirror of the reference's registry (reference/include/spmv.h:18-48) over the C ABI.
+
+    SpMV(kind_str, n_rows, n_cols, nnz, Ap, Aj, Ax, x, y)
+
+has the reference's argument list and meaning: the five arrays live on the device (here:
+CUDA torch tensors, used only as owners of device memory), `y` is fully overwritten with
+A @ x.  `SPMV_KINDS` plays the role of the X-macro table: label -> function with the
+8-argument per-kind signature (spmv.h:39).  An unknown label is an error, as in spmv.h:46-47
+(there: message on stderr + exit; here: the same message in a SpMVKindError).
+
+PyTorch is plumbing only (device memory, streams).  Every call goes through
+libspmvb200.so; there is no PyTorch or CPU implementation to fall back to.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import sys
+
+import torch
+
+from . import _lib
+
+
+class SpMVKindError(ValueError):
+    pass
+
+
+_OFF = {torch.int32: ("o32", 32), torch.int64: ("o64", 64)}
+_VAL = {torch.float32: ("f32", 32), torch.float64: ("f64", 64)}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr() if t is not None else 0)
+
+
+def _stream_ptr(stream=None):
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)
+
+
+def _check_tensors(Ap, Aj, Ax, x, y):
+    for name, t in (("Ap", Ap), ("Aj", Aj), ("Ax", Ax), ("x", x), ("y", y)):
+        if not t.is_cuda:
+            raise ValueError(f"{name} must be a CUDA tensor (device pointer), got {t.device}")
+        if not t.is_contiguous():
+            raise ValueError(f"{name} must be contiguous")
+    if Ap.dtype not in _OFF:
+        raise TypeError(f"offset type {Ap.dtype} unsupported (int32 / int64)")
+    if Aj.dtype != torch.int32:
+        raise TypeError("index type must be int32")
+    if Ax.dtype not in _VAL or x.dtype != Ax.dtype or y.dtype != Ax.dtype:
+        raise TypeError("Ax, x, y must share one dtype, float32 or float64")
+
+
+def _typed_call(kind: str, n_rows, n_cols, nnz, Ap, Aj, Ax, x, y, stream=None):
+    _check_tensors(Ap, Aj, Ax, x, y)
+    otag, _ = _OFF[Ap.dtype]
+    vtag, _ = _VAL[Ax.dtype]
+    fn = getattr(_lib.lib(), f"spmvb200_{kind}_i32_{otag}_{vtag}")
+    with torch.cuda.device(Ap.device):
+        st = fn(int(n_rows), int(n_cols), int(nnz), _ptr(Ap), _ptr(Aj), _ptr(Ax), _ptr(x), _ptr(y),
+                _stream_ptr(stream))
+    _lib.check(st, f"spmvb200_{kind}_i32_{otag}_{vtag}")
+
+
+def SpMV_merge(n_rows, n_cols, nnz, Ap, Aj, Ax, x, y, stream=None):
+    """Merge-path kernel (replaces SpMV_merge_based, merge_based/merge_based.cuh:22)."""
+    _typed_call("merge", n_rows, n_cols, nnz, Ap, Aj, Ax, x, y, stream)
+
+
+def SpMV_vector(n_rows, n_cols, nnz, Ap, Aj, Ax, x, y, stream=None):
+    """CSR-vector kernel (replaces SpMV_cusp_*, cusp/cusp.cuh:227)."""
+    _typed_call("vector", n_rows, n_cols, nnz, Ap, Aj, Ax, x, y, stream)
+
+
+def SpMV_light(n_rows, n_cols, nnz, Ap, Aj, Ax, x, y, stream=None):
+    """Dynamic-row kernel (replaces SpMV_light_vector / SpMV_light_warp, LightSpMV.cuh:379)."""
+    _typed_call("light", n_rows, n_cols, nnz, Ap, Aj, Ax, x, y, stream)
+
+
+def SpMV_auto(n_rows, n_cols, nnz, Ap, Aj, Ax, x, y, stream=None):
+    """Host selector: row statistics -> one of the kernels above."""
+    _typed_call("auto", n_rows, n_cols, nnz, Ap, Aj, Ax, x, y, stream)
+
+
+def SpMV_cusparse(n_rows, n_cols, nnz, Ap, Aj, Ax, x, y, stream=None):
+    """cuSPARSE baseline, setup hoisted (replaces SpMV_cusparse, cusparse.cuh:37)."""
+    _typed_call("cusparse", n_rows, n_cols, nnz, Ap, Aj, Ax, x, y, stream)
+
+
+# the X-macro table (spmv.h:18-27): label -> function
+SPMV_KINDS = {
+    "merge": SpMV_merge,
+    "vector": SpMV_vector,
+    "light": SpMV_light,
+    "auto": SpMV_auto,
+    "cusparse": SpMV_cusparse,
+}
+KIND_IDS = {"merge": _lib.KIND_MERGE, "vector": _lib.KIND_VECTOR, "light": _lib.KIND_LIGHT,
+            "auto": _lib.KIND_AUTO, "cusparse": _lib.KIND_CUSPARSE}
+
+
+def SpMV(kind_str, n_rows, n_cols, nnz, Ap, Aj, Ax, x, y, stream=None):
+    """reference/include/spmv.h:29-48."""
+    fn = SPMV_KINDS.get(kind_str)
+    if fn is None:
+        msg = f'SpMV kind "{kind_str}" is NOT SUPPROT'  # the reference's wording, spmv.h:46
+        print(msg, file=sys.stderr)
+        raise SpMVKindError(msg)
+    fn(n_rows, n_cols, nnz, Ap, Aj, Ax, x, y, stream)
+
+
+def spmv_ex(kind_str, Ap, Aj, Ax, x, y, n_cols=None, alpha_dev=None, y_peers=(), stream=None):
+    """Untyped entry (spmvb200_spmv): optional device alpha, optional peer replicas of y.
+    y_peers: iterable of raw device addresses (ints), each indexed like y."""
+    _check_tensors(Ap, Aj, Ax, x, y)
+    if kind_str not in KIND_IDS:
+        raise SpMVKindError(f'SpMV kind "{kind_str}" is NOT SUPPROT')
+    a = _lib.Args()
+    a.kind = KIND_IDS[kind_str]
+    a.offset_bits = _OFF[Ap.dtype][1]
+    a.value_bits = _VAL[Ax.dtype][1]
+    a.n_rows = Ap.numel() - 1
+    a.n_cols = int(n_cols) if n_cols is not None else x.numel()
+    a.nnz = Aj.numel()
+    a.Ap, a.Aj, a.Ax, a.x, a.y = (Ap.data_ptr(), Aj.data_ptr(), Ax.data_ptr(), x.data_ptr(),
+                                  y.data_ptr())
+    a.alpha_dev = alpha_dev.data_ptr() if alpha_dev is not None else None
+    peers = list(y_peers)
+    a.n_peers = len(peers)
+    arr = (C.c_void_p * max(1, len(peers)))(*peers)
+    a.y_peers = C.cast(arr, C.POINTER(C.c_void_p))
+    a.stream = (stream if stream is not None else torch.cuda.current_stream()).cuda_stream
+    with torch.cuda.device(Ap.device):
+        st = _lib.lib().spmvb200_spmv(C.byref(a))
+    _lib.check(st, f"spmvb200_spmv[{kind_str}]")
+
+
+def merge_path_partition(Ap, tile_items=None, stream=None):
+    """Row coordinates of the merge path on the tile diagonals (int32 CUDA tensor, tiles+1)."""
+    L = _lib.lib()
+    n_rows = Ap.numel() - 1
+    nnz = int(Ap[-1].item())
+    if tile_items is None:
+        tile_items = L.spmvb200_merge_tile_items(_OFF[Ap.dtype][1], 32)
+    tiles = (n_rows + nnz + tile_items - 1) // tile_items
+    out = torch.empty(tiles + 1, dtype=torch.int32, device=Ap.device)
+    fn = getattr(L, f"spmvb200_merge_path_partition_{_OFF[Ap.dtype][0]}")
+    with torch.cuda.device(Ap.device):
+        st = fn(n_rows, nnz, _ptr(Ap), int(tile_items), tiles + 1, _ptr(out), _stream_ptr(stream))
+    _lib.check(st, "spmvb200_merge_path_partition")
+    return out
+
+
+def row_split(Ap, parts: int, nnz=None, stream=None):
+    """nnz-balanced row boundaries (list of parts+1 ints) from the device merge-path search."""
+    L = _lib.lib()
+    n_rows = Ap.numel() - 1
+    if nnz is None:
+        nnz = int(Ap[-1].item())
+    out = (C.c_int64 * (parts + 1))()
+    fn = getattr(L, f"spmvb200_row_split_{_OFF[Ap.dtype][0]}")
+    with torch.cuda.device(Ap.device):
+        st = fn(n_rows, nnz, _ptr(Ap), parts, out, _stream_ptr(stream))
+    _lib.check(st, "spmvb200_row_split")
+    return [int(v) for v in out]
+
+
+def row_stats(Ap, nnz=None, stream=None):
+    L = _lib.lib()
+    n_rows = Ap.numel() - 1
+    if nnz is None:
+        nnz = int(Ap[-1].item())
+    st_out = _lib.RowStats()
+    with torch.cuda.device(Ap.device):
+        st = L.spmvb200_row_stats(_OFF[Ap.dtype][1], n_rows, nnz, _ptr(Ap), C.byref(st_out),
+                                  _stream_ptr(stream))
+    _lib.check(st, "spmvb200_row_stats")
+    return {f: getattr(st_out, f) for f, _ in _lib.RowStats._fields_}
+
+
+def set_option(name: str, value: int) -> None:
+    _lib.check(_lib.lib().spmvb200_set_option(name.encode(), int(value)), f"set_option({name})")
+
+
+def get_option(name: str) -> int:
+    return int(_lib.lib().spmvb200_get_option(name.encode()))
+
+
+def launch_count() -> int:
+    return int(_lib.lib().spmvb200_launch_count())

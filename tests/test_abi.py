@@ -1,0 +1,83 @@
+"""CPU suite: the C-ABI library builds for sm_100a, loads, and exports every symbol that
+include/spmv_b200.h declares.  No compute calls are made without a GPU."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    from spmv_samples_b200 import _lib
+    names = _lib.exported_symbols()
+    # 5 kinds x 4 type pairs + the untyped and auxiliary entry points
+    assert len([n for n in names if re.match(r"spmvb200_(merge|vector|light|auto|cusparse)_i32_", n)]) == 20
+    assert len(names) >= 40
+    missing = [n for n in names if not hasattr(built_lib, n)]
+    assert not missing, missing
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True,
+                         text=True, check=True).stdout
+    exported = set(re.findall(r" T (spmvb200_\w+)", out))
+    assert set(names) <= exported
+    # nothing but the declared ABI leaks out of the library
+    assert exported <= set(names), exported - set(names)
+
+
+def test_library_is_sm100a_with_tma_bulk_copies(built_lib):
+    from spmv_samples_b200 import _lib
+    r = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in r.stdout
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True,
+                          text=True).stdout
+    assert "merge_tile_kernel" in sass
+    assert "UBLKCP" in sass      # cp.async.bulk staging of the tile segments
+    assert "SYNCS" in sass       # mbarrier completion
+    assert re.search(r"LDG\.E\.[A-Z.]*128", sass)   # 128-bit loads of Aj / Ax
+
+
+def test_status_strings_and_options(built_lib):
+    assert built_lib.spmvb200_status_string(0) == b"ok"
+    assert b"aligned" in built_lib.spmvb200_status_string(2)
+    assert built_lib.spmvb200_version().startswith(b"spmvb200")
+    assert built_lib.spmvb200_get_option(b"l2_window") in (0, 1)
+    assert built_lib.spmvb200_set_option(b"no_such_option", 1) != 0
+    assert built_lib.spmvb200_merge_tile_items(32, 32) > 0
+
+
+def test_python_mirror_has_reference_surface():
+    from spmv_samples_b200 import spmv
+    assert set(spmv.SPMV_KINDS) == {"merge", "vector", "light", "auto", "cusparse"}
+    import inspect
+    params = list(inspect.signature(spmv.SpMV).parameters)
+    assert params[:9] == ["kind_str", "n_rows", "n_cols", "nnz", "Ap", "Aj", "Ax", "x", "y"]
+    for fn in spmv.SPMV_KINDS.values():
+        assert list(inspect.signature(fn).parameters)[:8] == [
+            "n_rows", "n_cols", "nnz", "Ap", "Aj", "Ax", "x", "y"]
+
+
+def test_unknown_kind_is_an_error(capsys):
+    from spmv_samples_b200 import spmv
+    with pytest.raises(spmv.SpMVKindError):
+        spmv.SpMV("no_such_kind", 0, 0, 0, None, None, None, None, None)
+    assert "NOT SUPPROT" in capsys.readouterr().err
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under spmv_samples_b200/, include/ or main.cu
+    may reference it, and there is no CPU fallback in the Python binding."""
+    bad = []
+    for base in ("spmv_samples_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            if "build" in dirpath.split(os.sep):
+                continue
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                    text = open(os.path.join(dirpath, f), errors="ignore").read()
+                    if re.search(r"^\s*(from|import)\s+oracle\b", text, re.M) or "liboracle" in text \
+                            or "libspmv_ref" in text:
+                        bad.append(os.path.join(dirpath, f))
+    assert not bad, bad

@@ -1,0 +1,354 @@
+"""GPU parity suite: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bars (BASELINE.json north_star): partition coordinates and row assignments bit-exact; y within
+|y - y_ref| <= 1e-5 * sum_j |a_ij x_j| per row for fp32 and 1e-13 for fp64, against an fp64
+host reference (oracle.cpu.spmv_fp64 / abs_scale, pinned to the reference in test_oracle.py).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import golden_cases, load_golden
+from oracle import cpu, generators as g
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+KINDS = ["merge", "vector", "light", "auto", "cusparse"]
+OURS = ["merge", "vector", "light", "auto"]
+TOL = {np.dtype(np.float32): 1e-5, np.dtype(np.float64): 1e-13}
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda(built_lib):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    yield
+    torch.cuda.synchronize()
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def run_kind(kind, Ap, Aj, Ax, x, n_cols=None):
+    from spmv_samples_b200 import spmv
+    n_rows = Ap.shape[0] - 1
+    n_cols = x.shape[0] if n_cols is None else n_cols
+    dAp, dAj, dAx, dx = dev(Ap), dev(Aj), dev(Ax), dev(x)
+    dy = torch.full((n_rows,), float("nan"), dtype=dAx.dtype, device="cuda")  # must be overwritten
+    spmv.SpMV(kind, n_rows, n_cols, int(Ap[-1]), dAp, dAj, dAx, dx, dy)
+    torch.cuda.synchronize()
+    return dy.cpu().numpy()
+
+
+def assert_within_tolerance(y, Ap, Aj, Ax, x, what=""):
+    y64 = cpu.spmv_fp64(Ap, Aj, Ax, x)
+    scale = cpu.abs_scale(Ap, Aj, Ax, x)
+    tol = TOL[np.dtype(Ax.dtype)]
+    err = np.abs(y.astype(np.float64) - y64)
+    bad = np.nonzero(~(err <= tol * scale))[0]
+    assert bad.size == 0, (f"{what}: {bad.size} rows out of tolerance, first {bad[:5]}, "
+                           f"err {err[bad[:5]]}, allowed {tol * scale[bad[:5]]}")
+
+
+# ------------------------------------------------------------------ golden fixtures
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("name", golden_cases())
+def test_golden_parity(name, kind):
+    d = load_golden(name)
+    Ap, Aj, Ax, x = d["Ap"], d["Aj"], d["Ax"], d["x"]
+    y = run_kind(kind, Ap, Aj, Ax, x)
+    tol = TOL[np.dtype(Ax.dtype)]
+    err = np.abs(y.astype(np.float64) - d["y_ref64"])
+    assert np.all(err <= tol * d["abs_ref"]), (name, kind, err.max())
+    if name == "lattice3x3":
+        assert y.tolist() == [2, 3, 2, 3, 4, 3, 2, 3, 2]   # device_spmv.cuh:128
+
+
+@pytest.mark.parametrize("kind", OURS + ["cusparse"])
+@pytest.mark.parametrize("name", ["rmat_s8", "ragged_300", "ragged_f64_200"])
+def test_golden_parity_int64_offsets(name, kind):
+    d = load_golden(name)
+    Ap = d["Ap"].astype(np.int64)
+    try:
+        y = run_kind(kind, Ap, d["Aj"], d["Ax"], d["x"])
+    except Exception as e:  # cuSPARSE may not take 64-bit offsets with 32-bit indices
+        if kind == "cusparse":
+            pytest.skip(f"cuSPARSE baseline rejected int64 offsets: {e}")
+        raise
+    err = np.abs(y.astype(np.float64) - d["y_ref64"])
+    assert np.all(err <= TOL[np.dtype(d["Ax"].dtype)] * d["abs_ref"])
+
+
+# ------------------------------------------------------------------ seeded families
+FAMILIES = {
+    "lap2d_256": lambda: g.lap2d(256),
+    "uniform_64k_x16": lambda: g.uniform_rows(65536, 65536, 16, 7),
+    "rmat_s16": lambda: g.rmat(16, 16, 5),
+    "longrow_f64_512x2048": lambda: g.uniform_rows(512, 65536, 2048, 9, dtype=np.float64),
+    "ragged_heavy": lambda: g.ragged(20000, 5000, 9.0, 1, heavy_rows=3, heavy_len=60000),
+    "ragged_mostly_empty": lambda: g.ragged(30000, 1000, 1.5, 2, empty_frac=0.8),
+    "ragged_f64": lambda: g.ragged(8000, 3000, 30.0, 3, dtype=np.float64, heavy_len=20000),
+    "rmat_s14_o64": lambda: g.rmat(14, 16, 8, offset_dtype=np.int64),
+}
+
+
+@pytest.mark.parametrize("kind", OURS)
+@pytest.mark.parametrize("family", sorted(FAMILIES))
+def test_family_parity(family, kind):
+    Ap, Aj, Ax = FAMILIES[family]()
+    n_cols = int(Aj.max()) + 1
+    x = g.gen_x(17, n_cols, Ax.dtype)
+    y = run_kind(kind, Ap, Aj, Ax, x)
+    assert_within_tolerance(y, Ap, Aj, Ax, x, f"{family}/{kind}")
+
+
+@pytest.mark.parametrize("family", ["uniform_64k_x16", "rmat_s16", "longrow_f64_512x2048"])
+def test_family_parity_cusparse_baseline(family):
+    Ap, Aj, Ax = FAMILIES[family]()
+    x = g.gen_x(17, int(Aj.max()) + 1, Ax.dtype)
+    y = run_kind("cusparse", Ap, Aj, Ax, x)
+    # the baseline is held to a looser bar: it is compared, not shipped
+    y64 = cpu.spmv_fp64(Ap, Aj, Ax, x)
+    scale = cpu.abs_scale(Ap, Aj, Ax, x)
+    assert np.all(np.abs(y - y64) <= 10 * TOL[np.dtype(Ax.dtype)] * scale + 1e-30)
+
+
+@pytest.mark.parametrize("width", [1, 2, 4, 8, 16, 32])
+@pytest.mark.parametrize("kind", ["vector", "light"])
+def test_every_subwarp_width(kind, width):
+    from spmv_samples_b200 import spmv
+    Ap, Aj, Ax = g.ragged(5000, 2000, 13.0, 4, heavy_len=3000)
+    x = g.gen_x(3, 2000)
+    opt = "vector_width" if kind == "vector" else "light_width"
+    spmv.set_option(opt, width)
+    try:
+        y = run_kind(kind, Ap, Aj, Ax, x)
+    finally:
+        spmv.set_option(opt, 0)
+    assert_within_tolerance(y, Ap, Aj, Ax, x, f"{kind} width {width}")
+
+
+# ------------------------------------------------------------------ edge cases
+def _csr(lens, n_cols, seed=0, dtype=np.float32, off=np.int32):
+    rng = np.random.default_rng(seed)
+    Ap = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=Ap[1:])
+    nnz = int(Ap[-1])
+    Aj = rng.integers(0, n_cols, nnz).astype(np.int32)
+    Ax = rng.uniform(-1, 1, nnz).astype(dtype)
+    return Ap.astype(off), Aj, Ax
+
+
+EDGE = {
+    "all_rows_empty": lambda: _csr([0] * 777, 10),
+    "single_row_single_nnz": lambda: _csr([1], 5),
+    "single_row_100k": lambda: _csr([100003], 4096),
+    "one_huge_row_between_empties": lambda: _csr([0] * 100 + [50001] + [0] * 100, 999),
+    "all_nnz_in_last_row": lambda: _csr([0] * 5000 + [7777], 100),
+    "all_nnz_in_first_row": lambda: _csr([7777] + [0] * 5000, 100),
+    "nnz_not_multiple_of_4": lambda: _csr([3, 1, 2, 5, 0, 7, 1], 9),
+    "exact_tile_multiple": lambda: _csr([15] * 128, 64),          # 128 rows + 1920 nnz = 2048
+    "tile_boundary_on_row_end": lambda: _csr([2047] + [2047], 64),
+    "n_cols_1": lambda: _csr([1, 0, 1, 1, 0] * 50, 1),
+    "two_tiles_one_row_each": lambda: _csr([2047, 2047, 1], 33),
+    "long_rows_f64": lambda: _csr([4099, 1, 4097, 0, 8191], 512, dtype=np.float64),
+    "o64_mixed": lambda: _csr([5, 0, 300, 2, 2, 9000, 1], 700, off=np.int64),
+}
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("case", sorted(EDGE))
+def test_edge_cases(case, kind):
+    Ap, Aj, Ax = EDGE[case]()
+    n_cols = {"n_cols_1": 1}.get(case, int(Aj.max()) + 1 if Aj.size else 10)
+    x = g.gen_x(23, n_cols, Ax.dtype)
+    if kind == "cusparse" and (Ap.dtype == np.int64):
+        pytest.skip("baseline: mixed index widths")
+    y = run_kind(kind, Ap, Aj, Ax, x, n_cols)
+    if kind == "cusparse":
+        y64 = cpu.spmv_fp64(Ap, Aj, Ax, x)
+        assert np.all(np.abs(y - y64) <= 10 * TOL[np.dtype(Ax.dtype)] * cpu.abs_scale(Ap, Aj, Ax, x) + 1e-30)
+    else:
+        assert_within_tolerance(y, Ap, Aj, Ax, x, f"{case}/{kind}")
+        if case == "all_rows_empty":
+            assert np.all(y == 0)   # empty rows give exactly 0 (SURVEY.md 8(b) semantics)
+
+
+@pytest.mark.parametrize("kind", OURS)
+def test_zero_rows_is_a_noop(kind):
+    from spmv_samples_b200 import spmv
+    Ap = torch.zeros(1, dtype=torch.int32, device="cuda")
+    e_i = torch.zeros(4, dtype=torch.int32, device="cuda")
+    e_f = torch.zeros(4, dtype=torch.float32, device="cuda")
+    y = torch.full((4,), 7.0, device="cuda")
+    spmv.SpMV(kind, 0, 4, 0, Ap, e_i, e_f, e_f, y)      # n_rows == 0
+    spmv.SpMV(kind, 4, 0, 0, torch.zeros(5, dtype=torch.int32, device="cuda"), e_i, e_f, e_f, y)
+    torch.cuda.synchronize()
+    assert torch.all(y == 7.0)   # dispatch_spmv_orig.cuh:564-570: nothing is written
+
+
+def test_misaligned_pointer_is_rejected():
+    from spmv_samples_b200 import spmv, _lib
+    Ap, Aj, Ax = g.uniform_rows(64, 64, 16, 1)
+    x = dev(g.gen_x(1, 64))
+    dAp, dAx = dev(Ap), dev(Ax)
+    buf = torch.zeros(Aj.size + 1, dtype=torch.int32, device="cuda")
+    buf[1:] = dev(Aj)
+    y = torch.zeros(64, device="cuda")
+    with pytest.raises(_lib.SpmvB200Error) as ei:
+        spmv.SpMV("merge", 64, 64, int(Ap[-1]), dAp, buf[1:], dAx, x, y)
+    assert ei.value.status == 2
+
+
+def test_negative_sizes_are_rejected():
+    from spmv_samples_b200 import spmv, _lib
+    t = torch.zeros(8, dtype=torch.int32, device="cuda")
+    f = torch.zeros(8, device="cuda")
+    with pytest.raises(_lib.SpmvB200Error) as ei:
+        spmv.SpMV("vector", -1, 4, 0, t, t, f, f, f)
+    assert ei.value.status == 1
+
+
+# ------------------------------------------------------------------ partition: bit-exact
+@pytest.mark.parametrize("off", [np.int32, np.int64])
+@pytest.mark.parametrize("family", ["rmat_s16", "ragged_heavy", "ragged_mostly_empty", "lap2d_256"])
+def test_partition_coordinates_bit_exact(family, off):
+    from spmv_samples_b200 import spmv
+    Ap, _, _ = FAMILIES[family]()
+    Ap = Ap.astype(off)
+    for tile in (2048, 896, 320, 1, 7):
+        if tile < 7 and Ap.shape[0] > 30000:
+            continue
+        got = spmv.merge_path_partition(dev(Ap), tile).cpu().numpy().astype(np.int64)
+        cx, cy = cpu.merge_tile_coords(Ap, tile)
+        assert np.array_equal(got, cx), (family, tile)
+        total = Ap.shape[0] - 1 + int(Ap[-1])
+        diag = np.minimum(np.arange(got.size, dtype=np.int64) * tile, total)
+        assert np.array_equal(diag - got, cy)
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_partition_matches_reference_golden(name):
+    from spmv_samples_b200 import spmv
+    d = load_golden(name)
+    for tile in (2048, 896, 320):
+        got = spmv.merge_path_partition(dev(d["Ap"]), tile).cpu().numpy()
+        assert np.array_equal(got, d[f"coords_{tile}"][:, 0])
+    if "path_all" in d:
+        got = spmv.merge_path_partition(dev(d["Ap"]), 1).cpu().numpy()
+        assert np.array_equal(got, d["path_all"][:, 0])
+
+
+@pytest.mark.parametrize("parts", [1, 2, 3, 4, 8])
+def test_row_split_bit_exact(parts):
+    from spmv_samples_b200 import spmv
+    for fam in ("rmat_s16", "ragged_heavy", "rmat_s14_o64"):
+        Ap, _, _ = FAMILIES[fam]()
+        got = spmv.row_split(dev(Ap), parts)
+        assert got == cpu.row_split(Ap, parts).tolist(), (fam, parts)
+
+
+# ------------------------------------------------------------------ generators: bit-exact
+def test_device_generators_match_host_restatement():
+    from spmv_samples_b200 import generate as gen
+    m = gen.lap2d(48)
+    Ap, Aj, Ax = g.lap2d(48)
+    assert np.array_equal(m.Ap.cpu().numpy(), Ap) and np.array_equal(m.Aj.cpu().numpy(), Aj)
+    assert np.array_equal(m.Ax.cpu().numpy(), Ax)
+    m = gen.uniform_rows(1000, 4096, 16, 77)
+    Ap, Aj, Ax = g.uniform_rows(1000, 4096, 16, 77)
+    assert np.array_equal(m.Ap.cpu().numpy(), Ap) and np.array_equal(m.Aj.cpu().numpy(), Aj)
+    assert np.array_equal(m.Ax.cpu().numpy(), Ax)
+    m = gen.uniform_rows(64, 4096, 2048, 5, dtype=torch.float64, offset=torch.int64)
+    Ap, Aj, Ax = g.uniform_rows(64, 4096, 2048, 5, dtype=np.float64, offset_dtype=np.int64)
+    assert np.array_equal(m.Ap.cpu().numpy(), Ap) and np.array_equal(m.Aj.cpu().numpy(), Aj)
+    assert np.array_equal(m.Ax.cpu().numpy(), Ax)
+    r, c = gen.rmat_edges(13, 99, 500, 20000)
+    rh, ch = g.rmat_edges(13, 99, 500, 20000)
+    assert np.array_equal(r.cpu().numpy(), rh) and np.array_equal(c.cpu().numpy(), ch)
+    for dt, ndt in ((torch.float32, np.float32), (torch.float64, np.float64)):
+        assert np.array_equal(gen.gen_x(5000, 31, dt).cpu().numpy(), g.gen_x(31, 5000, ndt))
+
+
+@pytest.mark.parametrize("off", [torch.int32, torch.int64])
+def test_device_rmat_csr_matches_host(off):
+    from spmv_samples_b200 import generate as gen
+    m = gen.rmat(14, 16, 3, offset=off)
+    Ap, Aj, Ax = g.rmat(14, 16, 3, offset_dtype=np.int64 if off == torch.int64 else np.int32)
+    assert np.array_equal(m.Ap.cpu().numpy(), Ap)
+    assert np.array_equal(m.Aj.cpu().numpy(), Aj)     # stable: generation order within a row
+    assert np.array_equal(m.Ax.cpu().numpy(), Ax)
+
+
+def test_device_coo_to_csr_with_values_matches_oracle():
+    from spmv_samples_b200 import generate as gen
+    rng = np.random.default_rng(5)
+    n_rows, nnz = 3000, 100000
+    rows = rng.integers(0, n_rows, nnz).astype(np.int32)
+    rows[rng.random(nnz) < 0.3] = 17          # a hot row
+    cols = rng.integers(0, 5000, nnz).astype(np.int32)
+    vals = rng.uniform(-1, 1, nnz).astype(np.float32)
+    Ap, Aj, Ax = gen.coo_to_csr(n_rows, dev(rows), dev(cols), dev(vals))
+    eAp, eAj, eAx = cpu.coo_to_csr(n_rows, rows, cols, vals)
+    assert np.array_equal(Ap.cpu().numpy(), eAp) and np.array_equal(Aj.cpu().numpy(), eAj)
+    assert np.array_equal(Ax.cpu().numpy(), eAx)
+
+
+# ------------------------------------------------------------------ alpha, peers, host API
+@pytest.mark.parametrize("kind", ["merge", "vector", "light"])
+def test_device_alpha_and_peer_replicas(kind):
+    from spmv_samples_b200 import spmv
+    Ap, Aj, Ax = g.ragged(6000, 1500, 8.0, 6, heavy_len=9000)
+    x = g.gen_x(4, 1500)
+    dAp, dAj, dAx, dx = dev(Ap), dev(Aj), dev(Ax), dev(x)
+    y = torch.empty(6000, device="cuda")
+    rep = [torch.full((6000 + 10,), float("nan"), device="cuda") for _ in range(3)]
+    alpha = torch.tensor([0.375], device="cuda")
+    # replicas receive the rows at an offset, the way a peer's x_next + row_begin does
+    peers = [r.data_ptr() + 4 * i * 3 for i, r in enumerate(rep)]
+    spmv.spmv_ex(kind, dAp, dAj, dAx, dx, y, alpha_dev=alpha, y_peers=peers)
+    torch.cuda.synchronize()
+    y_plain = run_kind(kind, Ap, Aj, Ax, x)
+    got = y.cpu().numpy()
+    scale = cpu.abs_scale(Ap, Aj, Ax, x)
+    assert np.all(np.abs(got.astype(np.float64) - 0.375 * y_plain) <= 0.375 * 1e-5 * scale)
+    for i, r in enumerate(rep):
+        assert np.array_equal(r[3 * i:3 * i + 6000].cpu().numpy(), got)   # bit-identical copies
+
+
+def test_host_buffer_matrix_object():
+    from spmv_samples_b200.matrix import CsrMatrix
+    Ap, Aj, Ax = g.rmat(13, 16, 2)
+    x = g.gen_x(8, 1 << 13)
+    m = CsrMatrix(1 << 13, 1 << 13, Ap, Aj, Ax)
+    for kind in OURS:
+        y = m.spmv(x, kind=kind)
+        assert_within_tolerance(y, Ap, Aj, Ax, x, f"CsrMatrix/{kind}")
+    m.close()
+
+
+def test_row_stats_and_selector():
+    from spmv_samples_b200 import spmv
+    Ap, _, _ = g.uniform_rows(10000, 10000, 16, 1)
+    st = spmv.row_stats(dev(Ap))
+    assert st["max_row_len"] == 16 and st["empty_rows"] == 0 and abs(st["mean_row_len"] - 16) < 1e-9
+    assert st["chosen_kind"] == 1 and st["chosen_width"] == 4          # regular -> vector, T=4
+    Ap, _, _ = g.rmat(14, 16, 3)
+    st = spmv.row_stats(dev(Ap))
+    lens = np.diff(Ap)
+    assert st["max_row_len"] == lens.max() and st["empty_rows"] == int((lens == 0).sum())
+    assert abs(st["std_row_len"] - lens.std()) < 1e-6 * max(1.0, lens.std())
+    assert st["chosen_kind"] == 0                                       # power law -> merge
+
+
+def test_repeated_calls_are_deterministic():
+    """The carry fixup is ordered, not atomic: the same input gives the same bits every time."""
+    Ap, Aj, Ax = g.ragged(20000, 5000, 9.0, 1, heavy_rows=3, heavy_len=60000)
+    x = g.gen_x(17, 5000)
+    for kind in ("merge", "vector"):
+        y0 = run_kind(kind, Ap, Aj, Ax, x)
+        for _ in range(3):
+            assert np.array_equal(run_kind(kind, Ap, Aj, Ax, x), y0)
