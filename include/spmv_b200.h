@@ -154,8 +154,8 @@ typedef struct {
     int32_t chosen_kind;  /* what "auto" runs for this matrix */
     int32_t chosen_width; /* lanes per row for vector / light */
 } spmvb200_row_stats_t;
-/* One pass over Ap on the device, result cached keyed on (Ap, n_rows, nnz).  Synchronises
- * the stream the first time a matrix is seen. */
+/* One pass over Ap on the device; synchronises the stream.  This call always recomputes (and
+ * refreshes the cache); the "auto" kind reuses the cached result keyed on (Ap, n_rows, nnz). */
 SPMVB200_API int spmvb200_row_stats(int offset_bits, int64_t n_rows, int64_t nnz, const void *Ap,
                                     spmvb200_row_stats_t *out, spmvb200_stream_t stream);
 

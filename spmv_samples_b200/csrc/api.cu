@@ -35,6 +35,8 @@ int run(int kind, int64_t n_rows, int64_t n_cols, int64_t nnz, const void *Ap, c
     if (n_rows < 0 || n_cols < 0 || nnz < 0) return SPMVB200_ERR_INVALID;
     if (n_rows > 0x7fffffffLL || n_cols > 0x7fffffffLL) return SPMVB200_ERR_INVALID;
     if (sizeof(OffT) == 4 && nnz > 0x7fffffffLL) return SPMVB200_ERR_INVALID;
+    // 32-bit offset arithmetic steps up to 1024 positions past a row end before it compares
+    if (sizeof(OffT) == 4 && nnz > 0x7fffffffLL - 4096) return SPMVB200_ERR_UNSUPPORTED;
     // the reference's no-op case (merge_based/dispatch_spmv_orig.cuh:564-570)
     if (n_rows == 0 || n_cols == 0) return SPMVB200_OK;
     if (!Ap || !y || (nnz > 0 && (!Aj || !Ax || !x))) return SPMVB200_ERR_INVALID;
@@ -178,8 +180,8 @@ int spmvb200_row_stats(int offset_bits, int64_t n_rows, int64_t nnz, const void 
                        spmvb200_row_stats_t *out, spmvb200_stream_t stream) {
     if (!out || n_rows < 0 || nnz < 0 || (!Ap && n_rows > 0)) return SPMVB200_ERR_INVALID;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (offset_bits == 32) return row_stats<int32_t>(n_rows, nnz, static_cast<const int32_t *>(Ap), out, s);
-    if (offset_bits == 64) return row_stats<int64_t>(n_rows, nnz, static_cast<const int64_t *>(Ap), out, s);
+    if (offset_bits == 32) return row_stats<int32_t>(n_rows, nnz, static_cast<const int32_t *>(Ap), out, s, false);
+    if (offset_bits == 64) return row_stats<int64_t>(n_rows, nnz, static_cast<const int64_t *>(Ap), out, s, false);
     return SPMVB200_ERR_UNSUPPORTED;
 }
 

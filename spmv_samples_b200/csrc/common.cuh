@@ -93,7 +93,7 @@ int launch_partition(int32_t n_rows, OffT nnz, const OffT *Ap, int64_t tile_item
                      int32_t *coords_x, cudaStream_t stream);
 template <typename OffT>
 int row_stats(int64_t n_rows, int64_t nnz, const OffT *Ap, spmvb200_row_stats_t *out,
-              cudaStream_t stream);
+              cudaStream_t stream, bool use_cache);
 int pick_width_from_mean(double mean_row_len);
 
 // Launch attribute helper: optional L2 access-policy window over x (option "l2_window").

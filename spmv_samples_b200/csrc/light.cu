@@ -9,6 +9,9 @@
 //     SpMV itself at 16.7M rows;
 //   * the grid is SMs x resident CTAs from the occupancy API -- the reference's launch has
 //     grid and block transposed;
+//   * a row far longer than its sub-warp is wide is reduced by the whole warp instead
+//     (row_dot.cuh warp_long_rows), the warp-level half of the load balancing the reference
+//     leaves entirely to the row counter;
 //   * no texture object, no __constant__ row count; x goes through L2 with an evict-last
 //     policy; the inner loop is the 128-bit one of row_dot.cuh.
 #include "common.cuh"
@@ -45,13 +48,18 @@ light_kernel(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
             const int64_t row = r0 + sub;
             const bool active = row < limit;
             ValT sum = (ValT)0;
+            OffT s = 0, e = 0;
             if (active) {
-                const OffT s = __ldg(Ap + row);
-                const OffT e = __ldg(Ap + row + 1);
-                sum = row_partial<T, OffT, ValT>(s, e, nnz, lane, Aj, Ax, x, pol_stream, pol_x);
+                s = __ldg(Ap + row);
+                e = __ldg(Ap + row + 1);
             }
+            const bool is_long = row_is_long<T, OffT>(e - s);
+            if (active && !is_long)
+                sum = row_partial<T, OffT, ValT>(s, e, nnz, lane, Aj, Ax, x, pol_stream, pol_x);
             sum = subwarp_sum<T>(sum);
-            if (active && lane == 0) store_y(y, peers, row, alpha * sum);
+            if (active && !is_long && lane == 0) store_y(y, peers, row, alpha * sum);
+            warp_long_rows<T, OffT, ValT>(is_long, s, e, row, nnz, Aj, Ax, x, y, peers, alpha,
+                                          pol_stream, pol_x);
         }
     }
 }

@@ -3,20 +3,29 @@
 // What it computes is what the reference's vendored CUB 1.15 merge-based SpMV computes
 // (reference/include/spmv/merge_based/dispatch_spmv_orig.cuh:109-229,
 //  agent_spmv_orig.cuh:454-760, agent_segment_fixup.cuh:229-358, thread_search.cuh:16-49):
-// the (row-end, nonzero) merge path of length n_rows + nnz is cut into equal tiles, each
-// tile reduces its nonzeros into the rows that end inside it and hands the unfinished
-// tail to a fixup pass.  How it does it is new:
-//   * a tile is 2048 path items (not 896/320) so that one CTA keeps 16-24 KB of Aj/Ax in
-//     flight and 8 CTAs/SM cover the HBM latency-bandwidth product of a B200 SM;
-//   * the tile's row offsets and its Aj / Ax segments are staged into shared memory with
-//     TMA 1-D bulk copies (cp.async.bulk -> UBLKCP) completing on one mbarrier, with an L2
-//     evict-first policy; x is gathered with an evict-last policy;
+// the (row-end, nonzero) merge path of length n_rows + nnz is cut into equal tiles by a
+// binary-search partition kernel, each tile reduces its nonzeros into the rows that end inside
+// it and hands the unfinished tail to a fixup pass.  How a tile is processed is new, because
+// a B200 SM has ~4x the HBM bandwidth per SM of the parts CUB's agent was tuned for and the
+// agent's per-thread path search + serial merge (about 45 scalar shared-memory operations per
+// thread) is shared-memory-issue bound here (first ncu capture: mio_throttle + short
+// scoreboard dominant, 75 thread instructions per path item, 16 % of the HBM roofline):
+//   * a tile is 2044 path items; its row offsets and its Aj / Ax segments are staged into
+//     shared memory with TMA 1-D bulk copies (cp.async.bulk -> UBLKCP) completing on one
+//     mbarrier, with an L2 evict-first policy;
+//   * every thread owns 8 consecutive staged nonzeros: 128-bit shared loads of Aj and Ax, x
+//     gathered with an L2 evict-last policy, products kept in registers;
+//   * rows are delimited by a byte flag per nonzero, scattered one thread per row end; the
+//     reduction is a segmented scan (serial in the thread, shuffles across the warp, one
+//     shared-memory hop across warps) -- no per-thread merge-path search at all;
+//   * the scanned values go back to shared memory once, and one thread per row end picks its
+//     row's total, so y is written coalesced;
 //   * only the row coordinate of each tile boundary is stored (int32); the nonzero
-//     coordinate is diagonal - row, which also makes the scratch 64-bit safe for free;
-//   * finished rows are stored straight from the merge loop; the cross-thread carry is a
-//     warp-shuffle segmented scan; the tile carry-out goes to a fixup kernel that is
-//     deterministic (run-head threads sum their run in tile order; no atomics, unlike
-//     agent_segment_fixup.cuh:257,269).
+//     coordinate is diagonal - row, which keeps the scratch 64-bit safe for free;
+//   * the tile carry-out goes to a fixup kernel that is deterministic (run-head threads sum
+//     their run in tile order; no atomics, unlike agent_segment_fixup.cuh:257,269).
+// Within a tile the work is bounded by construction (rows + nonzeros <= 2044), which is the
+// load-balance guarantee of the merge path; the in-tile phases are regular on top of it.
 #include <climits>
 
 #include "common.cuh"
@@ -27,12 +36,14 @@ namespace {
 
 constexpr int kMergeBlock = 256;
 constexpr int kMergeIPT = 8;
-constexpr int kMergeTile = kMergeBlock * kMergeIPT;
-constexpr int kPad = 8;  // slack for the 16-byte align-down shift and the sentinel
+constexpr int kSlots = kMergeBlock * kMergeIPT;  // staged elements per array
+constexpr int kMergeTile = kSlots - 4;           // path items per tile: room for the <=3-element
+                                                 // align-down shift of the bulk copies
+constexpr int kPad = 8;
 
 template <typename OffT, typename ValT>
 constexpr size_t merge_smem_bytes() {
-    return 16 + (size_t)(kMergeTile + kPad) * (sizeof(OffT) + sizeof(int32_t) + sizeof(ValT));
+    return 16 + (size_t)(kSlots + kPad) * sizeof(OffT) + (size_t)kSlots * (sizeof(int32_t) + sizeof(ValT) + 1);
 }
 
 // ---------------------------------------------------------------- partition (search) kernel
@@ -57,33 +68,56 @@ merge_partition_kernel(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap, in
     coords_x[t] = (int32_t)lo;
 }
 
-// stage count elements of g[gbeg ...) into s[(gbeg - a0) ...), a0 = gbeg aligned down to 16 B:
-// the 16-byte aligned interior by one bulk copy (thread 0), the ragged tail by plain loads.
-template <typename T>
+// stage `count` elements of g[gbeg ...) into s[(gbeg - a0) ...), a0 = gbeg aligned down to V
+// elements (V * sizeof(T) a multiple of 16): the aligned interior by one bulk copy (thread 0),
+// the ragged tail (fewer than V elements, or a whole tiny segment) by plain loads.
 struct StagePlan {
-    int64_t a0;          // first element of the bulk copy (aligned)
-    uint32_t bulk_bytes; // 0 = no bulk copy
-    int64_t tail_beg;    // first element loaded by threads
+    int64_t a0;           // first element of the bulk copy (aligned)
+    uint32_t bulk_elems;  // 0 = no bulk copy
+    int64_t tail_beg;     // first element loaded by threads
     int tail_cnt;
-    int shift;           // gbeg - a0
+    int shift;            // gbeg - a0
 };
-template <typename T>
-__device__ __forceinline__ StagePlan<T> plan_stage(int64_t gbeg, int count) {
-    constexpr int V = 16 / sizeof(T);
-    StagePlan<T> p;
+template <int V>
+__device__ __forceinline__ StagePlan plan_stage(int64_t gbeg, int count) {
+    StagePlan p;
     p.a0 = gbeg & ~(int64_t)(V - 1);
     p.shift = (int)(gbeg - p.a0);
     const int64_t gend = gbeg + count;
     const int64_t be = gend & ~(int64_t)(V - 1);
     if (be > p.a0 && count > 0) {
-        p.bulk_bytes = (uint32_t)((be - p.a0) * sizeof(T));
+        p.bulk_elems = (uint32_t)(be - p.a0);
         p.tail_beg = be;
     } else {
-        p.bulk_bytes = 0;
+        p.bulk_elems = 0;
         p.tail_beg = gbeg;
     }
     p.tail_cnt = (int)(gend - p.tail_beg);
     return p;
+}
+
+// 8 consecutive staged values -> registers (128-bit shared loads)
+__device__ __forceinline__ void lds8(const float *s, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4 *>(s);
+    const float4 b = *reinterpret_cast<const float4 *>(s + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void lds8(const double *s, double (&v)[8]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double2 a = *reinterpret_cast<const double2 *>(s + 2 * k);
+        v[2 * k] = a.x;
+        v[2 * k + 1] = a.y;
+    }
+}
+__device__ __forceinline__ void sts8(float *s, const float (&v)[8]) {
+    *reinterpret_cast<float4 *>(s) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4 *>(s + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void sts8(double *s, const double (&v)[8]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) *reinterpret_cast<double2 *>(s + 2 * k) = make_double2(v[2 * k], v[2 * k + 1]);
 }
 
 // ---------------------------------------------------------------------------- tile kernel
@@ -95,119 +129,99 @@ merge_tile_kernel(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
                   const ValT *__restrict__ alpha_dev, PeerOut peers,
                   const int32_t *__restrict__ coords_x, int32_t *__restrict__ carry_row,
                   ValT *__restrict__ carry_val) {
-    constexpr int TILE = kMergeTile;
     constexpr int IPT = kMergeIPT;
+    constexpr int VR = 16 / sizeof(OffT);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     OffT *s_rend = reinterpret_cast<OffT *>(smem_raw + 16);
-    int32_t *s_col = reinterpret_cast<int32_t *>(s_rend + TILE + kPad);
-    ValT *s_val = reinterpret_cast<ValT *>(s_col + TILE + kPad);
+    ValT *s_val = reinterpret_cast<ValT *>(s_rend + kSlots + kPad);
+    int32_t *s_col = reinterpret_cast<int32_t *>(s_val + kSlots);
+    unsigned char *s_flag = reinterpret_cast<unsigned char *>(s_col + kSlots);
     __shared__ ValT s_wval[kMergeBlock / 32];
     __shared__ int s_wflag[kMergeBlock / 32];
 
     const int tid = threadIdx.x;
     const int64_t tile = blockIdx.x;
     const int64_t total = (int64_t)n_rows + (int64_t)nnz;
-    const int64_t d0 = tile * TILE;
-    const int64_t d1 = d0 + TILE < total ? d0 + TILE : total;
+    const int64_t d0 = tile * kMergeTile;
+    const int64_t d1 = d0 + kMergeTile < total ? d0 + kMergeTile : total;
     const int32_t sx = __ldg(coords_x + tile);
     const int32_t ex = __ldg(coords_x + tile + 1);
     const int64_t sy = d0 - sx;
-    const int R = ex - sx;                     // rows that end inside this tile
-    const int Z = (int)((d1 - ex) - sy);       // nonzeros inside this tile
-    const int nr = R + (ex < n_rows ? 1 : 0);  // row ends staged (one past, for the open row)
+    const int R = ex - sx;                // rows that end inside this tile
+    const int Z = (int)((d1 - ex) - sy);  // nonzeros inside this tile
 
-    const StagePlan<OffT> pr = plan_stage<OffT>((int64_t)sx + 1, nr);
-    const StagePlan<int32_t> pc = plan_stage<int32_t>(sy, Z);
-    const StagePlan<ValT> pv = plan_stage<ValT>(sy, Z);
+    // Aj and Ax are staged with the same shift (sy mod 4), so slot s of either array holds
+    // tile-local nonzero s - shift
+    const StagePlan pr = plan_stage<VR>((int64_t)sx + 1, R);
+    const StagePlan pc = plan_stage<4>(sy, Z);
+    const int shift = pc.shift;
 
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
     }
+    // clear this thread's 8 row-start flags
+    *reinterpret_cast<uint2 *>(s_flag + tid * IPT) = make_uint2(0u, 0u);
     __syncthreads();
     if (tid == 0) {
         const uint64_t pol = policy_evict_first();
-        mbar_arrive_expect_tx(bar, pr.bulk_bytes + pc.bulk_bytes + pv.bulk_bytes);
-        if (pr.bulk_bytes) bulk_g2s(s_rend, Ap + pr.a0, pr.bulk_bytes, bar, pol);
-        if (pc.bulk_bytes) bulk_g2s(s_col, Aj + pc.a0, pc.bulk_bytes, bar, pol);
-        if (pv.bulk_bytes) bulk_g2s(s_val, Ax + pv.a0, pv.bulk_bytes, bar, pol);
-        // sentinel behind the staged row ends: "no further row ends here"
-        s_rend[pr.shift + nr] = (OffT)(sizeof(OffT) == 8 ? LLONG_MAX : INT_MAX);
+        mbar_arrive_expect_tx(bar, pr.bulk_elems * (uint32_t)sizeof(OffT) +
+                                       pc.bulk_elems * (uint32_t)(sizeof(int32_t) + sizeof(ValT)));
+        if (pr.bulk_elems) bulk_g2s(s_rend, Ap + pr.a0, pr.bulk_elems * (uint32_t)sizeof(OffT), bar, pol);
+        if (pc.bulk_elems) {
+            bulk_g2s(s_col, Aj + pc.a0, pc.bulk_elems * (uint32_t)sizeof(int32_t), bar, pol);
+            bulk_g2s(s_val, Ax + pc.a0, pc.bulk_elems * (uint32_t)sizeof(ValT), bar, pol);
+        }
     }
-    // ragged tails (fewer than one 16-byte vector each, or a whole tiny segment)
     if (tid < pr.tail_cnt) s_rend[pr.tail_beg - pr.a0 + tid] = __ldg(Ap + pr.tail_beg + tid);
-    if (tid < pc.tail_cnt) s_col[pc.tail_beg - pc.a0 + tid] = __ldg(Aj + pc.tail_beg + tid);
-    if (tid < pv.tail_cnt) s_val[pv.tail_beg - pv.a0 + tid] = __ldg(Ax + pv.tail_beg + tid);
-
+    if (tid < pc.tail_cnt) {
+        s_col[pc.tail_beg - pc.a0 + tid] = __ldg(Aj + pc.tail_beg + tid);
+        s_val[pc.tail_beg - pc.a0 + tid] = __ldg(Ax + pc.tail_beg + tid);
+    }
     const ValT alpha = alpha_dev ? __ldg(alpha_dev) : (ValT)1;
     const uint64_t pol_x = policy_evict_last();
 
     mbar_wait(bar, 0);
     __syncthreads();
 
-    // ---- products: s_val[i] *= x[s_col[i]], block-strided (bank-conflict free), all
-    // gathers of a thread issued before the first use
+    // ---- this thread's 8 consecutive slots: gather x (all loads issued before first use)
+    const OffT *rend = s_rend + pr.shift;
+    const int slot0 = tid * IPT;
+    ValT p[IPT];
     {
-        const int32_t *cc = s_col + pc.shift;
-        ValT *vv = s_val + pv.shift;
+        const int4 ca = *reinterpret_cast<const int4 *>(s_col + slot0);
+        const int4 cb = *reinterpret_cast<const int4 *>(s_col + slot0 + 4);
+        const int c[IPT] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
         ValT xv[IPT];
 #pragma unroll
         for (int k = 0; k < IPT; ++k) {
-            const int i = tid + k * kMergeBlock;
-            xv[k] = (i < Z) ? ldg_hint(x + cc[i], pol_x) : (ValT)0;
+            const int i = slot0 + k - shift;  // tile-local nonzero index
+            xv[k] = (i >= 0 && i < Z) ? ldg_hint(x + c[k], pol_x) : (ValT)0;
         }
+        // ---- row-start flags: the nonzero at which row sx+j+1 begins, one thread per row end
+        for (int j = tid; j < R; j += kMergeBlock) {
+            const int64_t q = (int64_t)rend[j] - sy;
+            if (q < Z) s_flag[(int)q + shift] = 1;
+        }
+        lds8(s_val + slot0, p);
 #pragma unroll
         for (int k = 0; k < IPT; ++k) {
-            const int i = tid + k * kMergeBlock;
-            if (i < Z) vv[i] *= xv[k];
+            const int i = slot0 + k - shift;
+            p[k] = (i >= 0 && i < Z) ? p[k] * xv[k] : (ValT)0;
         }
     }
     __syncthreads();
 
-    // ---- per-thread merge-path search inside the tile (diagonal tid*IPT)
-    const OffT *rend = s_rend + pr.shift;
-    const ValT *prod = s_val + pv.shift;
-    const int items = R + Z;
-    const int beg = min(tid * IPT, items);
-    const int n_my = min(IPT, items - beg);
-    const OffT syo = (OffT)sy;
-    int lo = max(beg - Z, 0), hi = min(beg, R);
-    while (lo < hi) {
-        const int p = (lo + hi) >> 1;
-        if (rend[p] <= syo + (OffT)(beg - p - 1)) lo = p + 1;
-        else hi = p;
-    }
-    int tx = lo, ty = beg - lo;
-
-    // ---- serial merge of this thread's items
-    ValT run = (ValT)0, first_part = (ValT)0;
-    int first_row = -1;
-    OffT next_end = rend[tx];
+    // ---- segmented scan.  pass 1: this thread's aggregate (saw a flag, sum since last flag)
+    const uint2 fw = *reinterpret_cast<const uint2 *>(s_flag + slot0);
+    const unsigned long long fbits = ((unsigned long long)fw.y << 32) | fw.x;  // byte k = flag k
+    int flag = fbits != 0ull;
+    ValT val = (ValT)0;
 #pragma unroll
-    for (int k = 0; k < IPT; ++k) {
-        if (k < n_my) {
-            if (syo + (OffT)ty < next_end) {
-                run += prod[ty];
-                ++ty;
-            } else {
-                if (first_row < 0) {
-                    first_row = tx;
-                    first_part = run;
-                } else {
-                    store_y(y, peers, (int64_t)sx + tx, alpha * run);
-                }
-                run = (ValT)0;
-                ++tx;
-                next_end = rend[tx];
-            }
-        }
-    }
+    for (int k = 0; k < IPT; ++k) val = ((fbits >> (8 * k)) & 1ull) ? p[k] : val + p[k];
 
-    // ---- segmented scan of (thread saw a row end, tail sum) across the block
     const int lane = tid & 31, warp = tid >> 5;
-    int flag = first_row >= 0;
-    ValT val = run;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const ValT pvv = __shfl_up_sync(0xffffffffu, val, d);
@@ -229,24 +243,36 @@ merge_tile_kernel(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
     }
     __syncthreads();
     ValT wv = (ValT)0;
-    int wf = 0;
 #pragma unroll
     for (int w = 0; w < kMergeBlock / 32; ++w) {
         if (w < warp) {
-            const int f = s_wflag[w];
             const ValT v = s_wval[w];
-            wv = f ? v : wv + v;
-            wf |= f;
+            wv = s_wflag[w] ? v : wv + v;
         }
     }
-    const ValT carry_in = ef ? ev : wv + ev;
-    if (first_row >= 0) store_y(y, peers, (int64_t)sx + first_row, alpha * (first_part + carry_in));
+    // pass 2: running sums from the carry-in, written back over the products
+    ValT run = ef ? ev : wv + ev;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        run = ((fbits >> (8 * k)) & 1ull) ? p[k] : run + p[k];
+        p[k] = run;
+    }
+    sts8(s_val + slot0, p);
+    __syncthreads();
 
-    if (tid == kMergeBlock - 1) {
-        // inclusive over the whole block = tail after the last row end of the tile
-        const ValT tot = flag ? val : wv + val;
+    // ---- one thread per row end: the row's total is the scan value at its last nonzero
+    const ValT *scan = s_val + shift;
+    for (int j = tid; j < R; j += kMergeBlock) {
+        const int q = (int)((int64_t)rend[j] - sy);
+        const int b = j > 0 ? (int)((int64_t)rend[j - 1] - sy) : 0;
+        const ValT sum = q > b ? scan[q - 1] : (ValT)0;
+        store_y(y, peers, (int64_t)sx + j, alpha * sum);
+    }
+    if (tid == 0) {
+        // nonzeros after the last row end of the tile belong to row ex: carry them out
+        const int lastq = R > 0 ? (int)((int64_t)rend[R - 1] - sy) : 0;
         carry_row[tile] = ex;
-        carry_val[tile] = tot;
+        carry_val[tile] = Z > lastq ? scan[Z - 1] : (ValT)0;
     }
 }
 
@@ -308,6 +334,11 @@ int launch_merge(const SpmvProblem<OffT, ValT> &p) {
     if (!attr_set) {
         SPMV_CUDA_TRY(cudaFuncSetAttribute(merge_tile_kernel<OffT, ValT>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // the whole unified array as shared memory: without this the driver's carveout left
+        // room for 6 CTAs/SM (ncu launch__occupancy_limit_shared_mem), the kernel wants 8
+        SPMV_CUDA_TRY(cudaFuncSetAttribute(merge_tile_kernel<OffT, ValT>,
+                                           cudaFuncAttributePreferredSharedMemoryCarveout,
+                                           (int)cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
     LaunchCfg lc;

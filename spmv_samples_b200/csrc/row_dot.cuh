@@ -5,16 +5,69 @@
 // and LightSpMV.cuh:147-170 compute (T lanes stride over one row, then a shuffle reduce),
 // but each lane moves four nonzeros per step with one 128-bit load of Aj and of Ax from a
 // 16-byte aligned position (the row start rounded down), masking the elements that fall
-// outside [row_start, row_end).  The reference only aligns for T == 32 and loads 4 bytes
-// per lane.
+// outside [row_start, row_end).  The
+// reference only aligns for T == 32 and loads 4 bytes per lane.
+//
+// Rows much longer than the sub-warp can chew (row_is_long) are handed to the whole warp by
+// the callers, so a power-law matrix does not serialise a 4-lane sub-warp on a 300K row.
 #pragma once
 
 #include "common.cuh"
 
 namespace spmvb200 {
 
-// Partial sum of row [s, e) seen by lane `lane` of a T-lane sub-warp.  nnz bounds the
-// arrays: the last vector of the matrix is read element-wise if it would run past them.
+template <typename ValT>
+struct Chunk {
+    int4 c;
+    typename Val4<ValT>::type v;
+    unsigned mask;  // bit k: element k lies inside the row
+};
+
+// Four consecutive nonzeros starting at the 4-aligned position p, masked to [s, e).
+// nnz bounds the arrays: the last vector of the matrix is read element-wise if it would run
+// past them.
+template <typename OffT, typename ValT>
+__device__ __forceinline__ Chunk<ValT> fetch_chunk(OffT p, OffT s, OffT e, OffT nnz,
+                                                   const int32_t *__restrict__ Aj,
+                                                   const ValT *__restrict__ Ax,
+                                                   uint64_t pol_stream) {
+    Chunk<ValT> ch;
+    ch.mask = 0;
+    ch.c = make_int4(0, 0, 0, 0);
+    ch.v.x = ch.v.y = ch.v.z = ch.v.w = (ValT)0;
+    if (p < e) {
+        ch.mask = ((p >= s) ? 1u : 0u) | ((p + 1 >= s && p + 1 < e) ? 2u : 0u) |
+                  ((p + 2 >= s && p + 2 < e) ? 4u : 0u) | ((p + 3 >= s && p + 3 < e) ? 8u : 0u);
+        if (p + 4 <= nnz) {
+            ch.c = ldg_stream_int4(Aj + p, pol_stream);
+            ch.v = ldg_stream_val4(Ax + p, pol_stream);
+        } else {
+            if (ch.mask & 1u) { ch.c.x = __ldg(Aj + p); ch.v.x = __ldg(Ax + p); }
+            if (ch.mask & 2u) { ch.c.y = __ldg(Aj + p + 1); ch.v.y = __ldg(Ax + p + 1); }
+            if (ch.mask & 4u) { ch.c.z = __ldg(Aj + p + 2); ch.v.z = __ldg(Ax + p + 2); }
+            if (ch.mask & 8u) { ch.c.w = __ldg(Aj + p + 3); ch.v.w = __ldg(Ax + p + 3); }
+        }
+    }
+    return ch;
+}
+
+// gather x for the valid elements (all four gathers issued before the first use) and
+// accumulate; the product is masked too, because a neighbouring row's value may be Inf/NaN
+template <typename ValT>
+__device__ __forceinline__ ValT consume_chunk(const Chunk<ValT> &ch, const ValT *__restrict__ x,
+                                              uint64_t pol_x, ValT sum) {
+    const ValT x0 = (ch.mask & 1u) ? ldg_hint(x + ch.c.x, pol_x) : (ValT)0;
+    const ValT x1 = (ch.mask & 2u) ? ldg_hint(x + ch.c.y, pol_x) : (ValT)0;
+    const ValT x2 = (ch.mask & 4u) ? ldg_hint(x + ch.c.z, pol_x) : (ValT)0;
+    const ValT x3 = (ch.mask & 8u) ? ldg_hint(x + ch.c.w, pol_x) : (ValT)0;
+    if (ch.mask & 1u) sum += ch.v.x * x0;
+    if (ch.mask & 2u) sum += ch.v.y * x1;
+    if (ch.mask & 4u) sum += ch.v.z * x2;
+    if (ch.mask & 8u) sum += ch.v.w * x3;
+    return sum;
+}
+
+// Partial sum of row [s, e) seen by lane `lane` of a T-lane group.
 template <int T, typename OffT, typename ValT>
 __device__ __forceinline__ ValT row_partial(OffT s, OffT e, OffT nnz, int lane,
                                             const int32_t *__restrict__ Aj,
@@ -23,32 +76,43 @@ __device__ __forceinline__ ValT row_partial(OffT s, OffT e, OffT nnz, int lane,
                                             uint64_t pol_x) {
     ValT sum = (ValT)0;
     const OffT a = s & ~(OffT)3;
+    // one chunk per trip: two in flight per trip was measured slower on every configuration
+    // (registers 32 -> 48-60, occupancy down; c2 273 -> 291 us, c4 298 -> 319 us)
     for (OffT p = a + (OffT)(4 * lane); p < e; p += (OffT)(4 * T)) {
-        if (p + 4 <= nnz) {
-            const int4 c = ldg_stream_int4(Aj + p, pol_stream);
-            const typename Val4<ValT>::type v = ldg_stream_val4(Ax + p, pol_stream);
-            const bool m0 = p >= s;  // p < e holds
-            const bool m1 = (p + 1 >= s) && (p + 1 < e);
-            const bool m2 = (p + 2 >= s) && (p + 2 < e);
-            const bool m3 = (p + 3 >= s) && (p + 3 < e);
-            const ValT x0 = m0 ? ldg_hint(x + c.x, pol_x) : (ValT)0;
-            const ValT x1 = m1 ? ldg_hint(x + c.y, pol_x) : (ValT)0;
-            const ValT x2 = m2 ? ldg_hint(x + c.z, pol_x) : (ValT)0;
-            const ValT x3 = m3 ? ldg_hint(x + c.w, pol_x) : (ValT)0;
-            // mask the product, not just the gather: a neighbouring row's value may be Inf/NaN
-            if (m0) sum += v.x * x0;
-            if (m1) sum += v.y * x1;
-            if (m2) sum += v.z * x2;
-            if (m3) sum += v.w * x3;
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const OffT q = p + k;
-                if (q >= s && q < e) sum += __ldg(Ax + q) * __ldg(x + __ldg(Aj + q));
-            }
-        }
+        const Chunk<ValT> c0 = fetch_chunk<OffT, ValT>(p, s, e, nnz, Aj, Ax, pol_stream);
+        sum = consume_chunk<ValT>(c0, x, pol_x, sum);
     }
     return sum;
+}
+
+// A row is "long" for a T-lane sub-warp when it would take more than 16 steps.
+template <int T, typename OffT>
+__device__ __forceinline__ bool row_is_long(OffT len) {
+    return T < 32 && len > (OffT)(64 * T);
+}
+
+// The long rows of one warp step, each reduced by all 32 lanes.  `is_long` is per sub-warp;
+// s, e, row are the sub-warp's values.  Returns nothing: stores directly.
+template <int T, typename OffT, typename ValT>
+__device__ __forceinline__ void warp_long_rows(bool is_long, OffT s, OffT e, int64_t row, OffT nnz,
+                                               const int32_t *__restrict__ Aj,
+                                               const ValT *__restrict__ Ax,
+                                               const ValT *__restrict__ x, ValT *__restrict__ y,
+                                               const PeerOut &peers, ValT alpha, uint64_t pol_stream,
+                                               uint64_t pol_x) {
+    if (T == 32) return;
+    const int wlane = threadIdx.x & 31;
+    unsigned todo = __ballot_sync(0xffffffffu, is_long && (wlane & (T - 1)) == 0);
+    while (todo) {
+        const int leader = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const OffT ls = __shfl_sync(0xffffffffu, s, leader);
+        const OffT le = __shfl_sync(0xffffffffu, e, leader);
+        const int64_t lrow = __shfl_sync(0xffffffffu, row, leader);
+        ValT ps = row_partial<32, OffT, ValT>(ls, le, nnz, wlane, Aj, Ax, x, pol_stream, pol_x);
+        ps = subwarp_sum<32>(ps);
+        if (wlane == 0) store_y(y, peers, lrow, alpha * ps);
+    }
 }
 
 }  // namespace spmvb200

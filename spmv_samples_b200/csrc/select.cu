@@ -86,11 +86,11 @@ void stats_cache_clear() {
 
 template <typename OffT>
 int row_stats(int64_t n_rows, int64_t nnz, const OffT *Ap, spmvb200_row_stats_t *out,
-              cudaStream_t stream) {
+              cudaStream_t stream, bool use_cache) {
     int dev = -1;
     SPMV_CUDA_TRY(cudaGetDevice(&dev));
     const StatsKey key{dev, (const void *)Ap, n_rows, nnz};
-    {
+    if (use_cache) {
         std::lock_guard<std::mutex> lk(g_stats_mu);
         auto it = g_stats.find(key);
         if (it != g_stats.end()) {
@@ -132,14 +132,14 @@ int row_stats(int64_t n_rows, int64_t nnz, const OffT *Ap, spmvb200_row_stats_t 
     *out = st;
     return SPMVB200_OK;
 }
-template int row_stats<int32_t>(int64_t, int64_t, const int32_t *, spmvb200_row_stats_t *, cudaStream_t);
-template int row_stats<int64_t>(int64_t, int64_t, const int64_t *, spmvb200_row_stats_t *, cudaStream_t);
+template int row_stats<int32_t>(int64_t, int64_t, const int32_t *, spmvb200_row_stats_t *, cudaStream_t, bool);
+template int row_stats<int64_t>(int64_t, int64_t, const int64_t *, spmvb200_row_stats_t *, cudaStream_t, bool);
 
 template <typename OffT, typename ValT>
 int launch_auto(const SpmvProblem<OffT, ValT> &p) {
     if (p.n_rows <= 0) return SPMVB200_OK;
     spmvb200_row_stats_t st;
-    SPMV_TRY(row_stats<OffT>(p.n_rows, (int64_t)p.nnz, p.Ap, &st, p.stream));
+    SPMV_TRY(row_stats<OffT>(p.n_rows, (int64_t)p.nnz, p.Ap, &st, p.stream, true));
     switch (st.chosen_kind) {
         case SPMVB200_KIND_VECTOR: return launch_vector<OffT, ValT>(p, st.chosen_width);
         case SPMVB200_KIND_LIGHT: return launch_light<OffT, ValT>(p, st.chosen_width);
@@ -167,6 +167,7 @@ struct CusparsePlan {
     void *buffer = nullptr;
     size_t buffer_bytes = 0;
     bool valid = false;
+    bool preprocessed = false;
 };
 std::mutex g_cs_mu;
 CusparsePlan g_plan;
@@ -209,7 +210,11 @@ int launch_cusparse(const SpmvProblem<OffT, ValT> &p) {
     const cusparseIndexType_t ot = sizeof(OffT) == 4 ? CUSPARSE_INDEX_32I : CUSPARSE_INDEX_64I;
     const ValT one = (ValT)1, zero = (ValT)0;
     CusparsePlan &pl = g_plan;
-    const bool hit = pl.valid && pl.dev == dev && pl.Ap == p.Ap && pl.Aj == p.Aj && pl.Ax == p.Ax &&
+    // a preprocessed plan depends on the matrix CONTENTS, which a pointer key cannot see
+    // (allocators hand the same addresses out again); it is only reused while the option
+    // that asked for it is still on
+    const bool want_pre = option_get("cusparse_preprocess", 0) > 0;
+    const bool hit = pl.valid && pl.preprocessed == want_pre && pl.dev == dev && pl.Ap == p.Ap && pl.Aj == p.Aj && pl.Ax == p.Ax &&
                      pl.n_rows == p.n_rows && pl.n_cols == p.n_cols && pl.nnz == (int64_t)p.nnz &&
                      pl.off_bits == (int)sizeof(OffT) * 8 && pl.val_bits == (int)sizeof(ValT) * 8;
     if (!hit) {
@@ -230,9 +235,11 @@ int launch_cusparse(const SpmvProblem<OffT, ValT> &p) {
                                                   pl.mat, pl.vx, &zero, pl.vy, vt,
                                                   CUSPARSE_SPMV_ALG_DEFAULT, &pl.buffer_bytes));
         SPMV_CUDA_TRY(cudaMalloc(&pl.buffer, pl.buffer_bytes ? pl.buffer_bytes : 16));
-        SPMV_CUSPARSE_TRY(cusparseSpMV_preprocess(pl.handle, CUSPARSE_OPERATION_NON_TRANSPOSE, &one,
-                                                  pl.mat, pl.vx, &zero, pl.vy, vt,
-                                                  CUSPARSE_SPMV_ALG_DEFAULT, pl.buffer));
+        pl.preprocessed = option_get("cusparse_preprocess", 0) > 0;
+        if (pl.preprocessed)
+            SPMV_CUSPARSE_TRY(cusparseSpMV_preprocess(pl.handle, CUSPARSE_OPERATION_NON_TRANSPOSE,
+                                                      &one, pl.mat, pl.vx, &zero, pl.vy, vt,
+                                                      CUSPARSE_SPMV_ALG_DEFAULT, pl.buffer));
         pl.valid = true;
     }
     SPMV_CUSPARSE_TRY(cusparseSetStream(pl.handle, p.stream));

@@ -28,17 +28,21 @@ vector_kernel(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
     const bool active = row < n_rows;
     const uint64_t pol_stream = policy_evict_first();
     const uint64_t pol_x = policy_evict_last();
+    const ValT alpha = alpha_dev ? __ldg(alpha_dev) : (ValT)1;
     ValT sum = (ValT)0;
+    OffT s = 0, e = 0;
     if (active) {
-        const OffT s = __ldg(Ap + row);
-        const OffT e = __ldg(Ap + row + 1);
+        s = __ldg(Ap + row);
+        e = __ldg(Ap + row + 1);
+    }
+    // rows far longer than the sub-warp is wide go to the whole warp afterwards
+    const bool is_long = row_is_long<T, OffT>(e - s);
+    if (active && !is_long)
         sum = row_partial<T, OffT, ValT>(s, e, nnz, lane, Aj, Ax, x, pol_stream, pol_x);
-    }
     sum = subwarp_sum<T>(sum);
-    if (active && lane == 0) {
-        const ValT alpha = alpha_dev ? __ldg(alpha_dev) : (ValT)1;
-        store_y(y, peers, row, alpha * sum);
-    }
+    if (active && !is_long && lane == 0) store_y(y, peers, row, alpha * sum);
+    warp_long_rows<T, OffT, ValT>(is_long, s, e, row, nnz, Aj, Ax, x, y, peers, alpha, pol_stream,
+                                  pol_x);
 }
 
 template <int T, typename OffT, typename ValT>

@@ -129,7 +129,8 @@ def test_full_size_config(cfg):
 
     # 5. partition invariants at the kernel's own tile size
     cx = spmv.merge_path_partition(m.Ap).long()
-    tile = 2048
+    from spmv_samples_b200 import _lib
+    tile = int(_lib.lib().spmvb200_merge_tile_items(64 if m.Ap.dtype == torch.int64 else 32, 32))
     total_items = m.n_rows + m.nnz
     diag = torch.clamp(torch.arange(cx.numel(), device="cuda") * tile, max=total_items)
     cy = diag - cx

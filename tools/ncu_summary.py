@@ -1,0 +1,29 @@
+"""Summarise an .ncu-rep (raw page) into the handful of numbers the roofline argument needs."""
+import csv, subprocess, sys, io
+rep = sys.argv[1]
+out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(out)))
+hdr, units = rows[0], rows[1]
+want = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'dram__throughput.avg.pct_of_peak_sustained_elapsed', 'lts__t_sector_hit_rate.pct',
+        'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__throughput.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__t_sector_hit_rate.pct', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread',
+        'launch__occupancy_limit_shared_mem', 'launch__occupancy_limit_registers', 'launch__occupancy_limit_warps',
+        'launch__grid_size', 'launch__block_size', 'launch__shared_mem_per_block_dynamic',
+        'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'lts__t_sectors_srcunit_tex_op_read.sum',
+        'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum',
+        'smsp__average_warps_issue_stalled']
+for vals in rows[2:]:
+    print("-" * 100)
+    for i, h in enumerate(hdr):
+        if any(h == w or (w.startswith('smsp__average_warps_issue_stalled') and h.startswith(w) and h.endswith('per_issue_active.ratio')) for w in want):
+            v = vals[i]
+            if h.startswith('smsp__average_warps_issue_stalled'):
+                try:
+                    if float(v) < 1.0: continue
+                except ValueError:
+                    pass
+            print(f"{h:88s} {units[i]:16s} {v}")
