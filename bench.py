@@ -1,0 +1,455 @@
+#!/usr/bin/env python
+"""bench.py -- the contract benchmark.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload c5|c1..c4] [--kind auto|merge|vector|light]
+                    [--exchange p2p|nccl] [--override SIZE]
+
+Workload (BASELINE.json configs[4], the configuration the 1/2/4/8-GPU metric is quoted on):
+R-MAT scale 27, edge factor 16 (134M rows, 2^31 nonzeros, int64 offsets, fp32), row-sharded
+over N GPUs by nnz-balanced merge-path splits; a "step" is one power-iteration SpMV
+x <- A x / ||A x|| over the whole matrix, including the exchange of the new x between GPUs.
+The matrix (19.3 GB) fits one GPU, so N = 1 runs the same workload; total work is fixed as N
+grows ("strong" scaling).
+
+One JSON line on stdout (rank 0):
+  value      whole-job GFLOP/s = 2 * nnz_total * K / t, t = CUDA-event time of K steps, max over
+             ranks, inputs resident in HBM
+  gbs        the same as effective GB/s on the algorithmic byte count
+  e2e        the same metric through the host-buffer API (CsrMatrix.spmv): x from pinned host
+             memory to the device, kernel, y back to the host, every step
+  roofline   dominant kernel (rank 0): algorithmic bytes of its launch / its CUDA-event duration,
+             against the measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline  the reference's CPU CSR loop (oracle/_ref when built, else the oracle port) on
+             the host cores, on a bounded row sample of the same matrix
+
+`--impl reference` times that CPU path alone (rank 0 only) and prints the same line with
+"impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "SpMV GFLOP/s and achieved HBM GB/s vs roofline at 1/2/4/8 B200"
+UNIT = "GFLOP/s"
+SEED = 0x5EEDB200
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=100)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--workload", default="c5", choices=["c1", "c2", "c3", "c4", "c5"])
+    p.add_argument("--override", type=int, default=0,
+                   help="shrink the workload (R-MAT scale / rows / grid); development only")
+    p.add_argument("--kind", default="auto")
+    p.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
+    p.add_argument("--e2e-steps", type=int, default=10)
+    p.add_argument("--cpu-seconds", type=float, default=15.0,
+                   help="budget of the cpu_baseline leg (own arm)")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def measured_peak():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def workload_desc(name, override):
+    from spmv_samples_b200 import generate
+    d = generate.CONFIGS[name]["desc"]
+    return d + (f" [override {override}]" if override else "")
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """SM clock, max clock and throttle reasons of one GPU, sampled during the timed region."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index, period=0.01):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._halt.is_set():
+            try:
+                self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                try:
+                    r = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    r = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def finish(self):
+        self._halt.set()
+        if self.is_alive():
+            self.join(timeout=1.0)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# --------------------------------------------------------------------------- CPU leg
+def build_row_sample(m, sample_nnz_target, n_blocks=16):
+    """16 equally spaced blocks of consecutive rows of the workload matrix, concatenated into one
+    CSR on the host (offsets rebased to 0, which changes no arithmetic)."""
+    import numpy as np
+    import torch
+
+    per_block = max(1, sample_nnz_target // n_blocks)
+    Ap_full = m.Ap
+    pieces_Ap, pieces_Aj, pieces_Ax = [np.zeros(1, dtype=np.int64)], [], []
+    base = 0
+    rows_total = 0
+    for b in range(n_blocks):
+        r0 = (m.n_rows * b) // n_blocks
+        r_hi = (m.n_rows * (b + 1)) // n_blocks
+        if r_hi <= r0:
+            continue
+        k0 = int(Ap_full[r0].item())
+        target = torch.tensor([k0 + per_block], device=Ap_full.device, dtype=Ap_full.dtype)
+        r1 = int(torch.searchsorted(Ap_full[r0:r_hi + 1], target, right=True).item()) - 1 + r0
+        r1 = max(r0 + 1, min(r1, r_hi))
+        k1 = int(Ap_full[r1].item())
+        pieces_Ap.append((Ap_full[r0 + 1:r1 + 1].to(torch.int64) - k0 + base).cpu().numpy())
+        pieces_Aj.append(m.Aj[k0:k1].cpu().numpy())
+        pieces_Ax.append(m.Ax[k0:k1].cpu().numpy())
+        base += k1 - k0
+        rows_total += r1 - r0
+    Ap = np.concatenate(pieces_Ap)
+    Aj = np.ascontiguousarray(np.concatenate(pieces_Aj))
+    Ax = np.ascontiguousarray(np.concatenate(pieces_Ax))
+    if m.Ap.dtype == torch.int32:
+        Ap = Ap.astype(np.int32)
+    return Ap, Aj, Ax, rows_total
+
+
+def cpu_reference_leg(global_csr, x_dev, steps, warmup, seconds_budget, sample_nnz_target=1 << 26):
+    """Time the reference's CPU CSR loop on a bounded sample of the matrix, all host threads,
+    for exactly `steps` timed calls after `warmup`.  The sample (see build_row_sample) is shrunk
+    until warmup + steps calls fit the time budget; x is the full vector, so the gathers miss
+    the CPU caches the way the full problem's do.  Returns (gflops, info dict)."""
+    import numpy as np
+
+    from oracle import cpu
+
+    x = x_dev.cpu().numpy()
+    threads = os.cpu_count() or 1
+    total = warmup + steps
+    target = sample_nnz_target
+    while True:
+        Ap, Aj, Ax, rows_total = build_row_sample(global_csr, target)
+        nnz_s = int(Ap[-1])
+        use_ref = cpu.have_ref() and not (Ap.dtype == np.int64 and Ax.dtype == np.float64)
+        run = (lambda: cpu.ref_spmv_mt(Ap, Aj, Ax, x, threads)) if use_ref else \
+              (lambda: cpu.spmv_mt(Ap, Aj, Ax, x, threads))
+        run()                                 # first touch
+        t0 = time.perf_counter()
+        _, used = run()                       # calibration
+        t_one = time.perf_counter() - t0
+        if t_one * total <= seconds_budget or target <= (1 << 20):
+            break
+        target = max(1 << 20, int(target * seconds_budget / (t_one * total) * 0.8))
+    for _ in range(max(0, warmup - 2)):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run()
+    dt = (time.perf_counter() - t0) / steps
+    # the reference as shipped is single threaded: time that too, once
+    t0 = time.perf_counter()
+    if use_ref:
+        cpu.ref_spmv(Ap, Aj, Ax, x)
+    else:
+        cpu.spmv(Ap, Aj, Ax, x)
+    dt1 = time.perf_counter() - t0
+    info = {
+        "kind": "reference" if use_ref else "port",
+        "cores": int(used),
+        "host_cores": int(threads),
+        "sample": f"{rows_total} rows / {nnz_s} nonzeros in 16 equally spaced row blocks of the "
+                  f"workload matrix, full-length x, {steps} timed calls of "
+                  + ("reference SpMV_cpu_navie (oracle/_ref) on row blocks from all host threads"
+                     if use_ref else "the oracle port of SpMV_cpu_navie, row blocks on all host threads"),
+        "single_thread_value": 2.0 * nnz_s / dt1 / 1e9,
+        "steps": steps,
+        "ms_per_step": dt * 1e3,
+    }
+    return 2.0 * nnz_s / dt / 1e9, info
+
+
+# --------------------------------------------------------------------------- reference arm
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return 0
+    import torch
+
+    from spmv_samples_b200 import generate
+    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+    if not torch.cuda.is_available():
+        # the matrix generator is a device kernel; without a GPU fall back to the host
+        # restatement at a scale the host can build
+        from oracle import generators as g
+        import numpy as np
+        scale = 20
+        Ap, Aj, Ax = g.rmat(scale, 16, SEED, offset_dtype=np.int64)
+        m = generate.Csr(1 << scale, 1 << scale, int(Ap[-1]), torch.from_numpy(Ap), torch.from_numpy(Aj),
+                         torch.from_numpy(Ax), f"rmat_s{scale} (host generated: no GPU)")
+        x = torch.from_numpy(g.gen_x(SEED, 1 << scale))
+        note = f"no GPU: R-MAT scale {scale} generated on the host instead of the workload"
+    else:
+        torch.cuda.set_device(0)
+        m = generate.make_config(args.workload, SEED, scale_override=args.override or None)
+        x = generate.gen_x(m.n_cols, SEED, m.Ax.dtype)
+        note = None
+    value, info = cpu_reference_leg(m, x, args.steps, args.warmup, seconds_budget=150.0)
+    info["value"] = value
+    info["unit"] = UNIT
+    line.update({
+        "value": value,
+        "ms_per_step": info["ms_per_step"],
+        "steps": info["steps"],
+        "config": {"workload": workload_desc(args.workload, args.override), "seed": SEED,
+                   "step": "one CPU CSR SpMV over the bounded sample", "note": note},
+        "cpu_baseline": info,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    })
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------- own arm
+def own_arm(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from spmv_samples_b200 import _lib, generate, spmv
+    from spmv_samples_b200.dist import PowerIteration, shard_rows
+    from spmv_samples_b200.matrix import CsrMatrix
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path "
+                         "(use --impl reference for the CPU baseline)")
+    _lib.lib()
+    spmv.set_option("time_main_kernel", 1)
+    peak, peak_src = measured_peak()
+
+    # ---- the matrix: every rank builds the global CSR on its own GPU, keeps its rows
+    t_gen = time.perf_counter()
+    gm = generate.make_config(args.workload, SEED, scale_override=args.override or None)
+    n, n_cols, nnz_total = gm.n_rows, gm.n_cols, gm.nnz
+    if n != n_cols:
+        raise SystemExit("power iteration needs a square matrix")
+    alg_bytes_total = gm.algorithmic_bytes()
+    stats = spmv.row_stats(gm.Ap, nnz=gm.nnz)
+    shard = shard_rows(gm, rank, world)
+    x_for_cpu = generate.gen_x(n_cols, SEED, gm.Ax.dtype) if (rank == 0 and world == 1) else None
+    cpu_info = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            v, cpu_info = cpu_reference_leg(gm, x_for_cpu, steps=3, warmup=1,
+                                            seconds_budget=args.cpu_seconds)
+            cpu_info["value"] = v
+            cpu_info["unit"] = UNIT
+        except Exception as e:  # the baseline is reported, never required
+            cpu_info = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
+                        "sample": f"failed: {e}"}
+    if world > 1:
+        del gm
+        torch.cuda.empty_cache()
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t_gen
+    local = shard.csr
+
+    it = PowerIteration(shard, n, kind=args.kind, exchange=args.exchange)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up, then K timed steps between barriers, CUDA events, max over ranks
+    for _ in range(max(args.warmup, 3)):
+        it.step()
+    barrier()
+    d_ms, d_n = C_double(), C_int64()
+    import ctypes
+    _lib.lib().spmvb200_main_kernel_time(ctypes.byref(d_ms), ctypes.byref(d_n))   # reset the kernel timer
+    launches0 = spmv.launch_count()
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        it.step()
+    e1.record()
+    barrier()
+    clocks = sampler.finish()
+    elapsed_ms = e0.elapsed_time(e1)
+    launches = spmv.launch_count() - launches0
+    _lib.lib().spmvb200_main_kernel_time(ctypes.byref(d_ms), ctypes.byref(d_n))
+    kern_ms = d_ms.value / max(d_n.value, 1)
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    sec = elapsed_ms * 1e-3
+    value = 2.0 * nnz_total * args.steps / sec / 1e9
+    gbs = alg_bytes_total * args.steps / sec / 1e9
+    eig = it.eigen_estimate()
+
+    # ---- roofline of the dominant kernel on rank 0's shard
+    alg_bytes_local = local.algorithmic_bytes()
+    achieved = alg_bytes_local / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get(f"{args.workload}@{world}")
+    except Exception:
+        pass
+
+    # ---- e2e: the host-buffer API, x H2D + kernel + y D2H every step, pinned host memory
+    e2e = None
+    if args.e2e_steps > 0:
+        mat = CsrMatrix.from_device(local)
+        xh = torch.empty(n_cols, dtype=local.Ax.dtype, pin_memory=True)
+        yh = torch.empty(local.n_rows, dtype=local.Ax.dtype, pin_memory=True)
+        xh.copy_(it.current_x().cpu())
+        xn, yn = xh.numpy(), yh.numpy()
+        for _ in range(2):
+            mat.spmv(xn, yn, kind=args.kind)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            mat.spmv(xn, yn, kind=args.kind)
+        dt = time.perf_counter() - t0
+        td = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        dt = float(td.item())
+        e2e = {"value": 2.0 * nnz_total * args.e2e_steps / dt / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": int(n_cols * xh.element_size()),
+               "d2h_bytes_per_step": int(local.n_rows * yh.element_size()),
+               "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
+               "api": "spmv_samples_b200.matrix.CsrMatrix.spmv (spmvb200_matrix_spmv_host): "
+                      "matrix resident (uploaded once, as reference main.cu:55-69), per-rank "
+                      "x H2D + SpMV + y D2H per step"}
+        mat.close()
+
+    it.close()
+    if rank == 0:
+        kind_names = {0: "merge", 1: "vector", 2: "light", 3: "auto", 4: "cusparse"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32"
+            if local.Ax.dtype == torch.float32 else "f64", "data": "synthetic",
+            "gbs": gbs, "roofline_frac_step": gbs / peak / world,
+            "config": {
+                "workload": workload_desc(args.workload, args.override), "seed": SEED,
+                "rows": n, "nnz": nnz_total, "offset_bits": local.Ap.element_size() * 8,
+                "algorithmic_bytes_per_spmv": alg_bytes_total,
+                "step": "one power-iteration SpMV (x <- A x / ||A x||) over the whole matrix, "
+                        "incl. x exchange and norm",
+                "kind": args.kind, "selected_kernel": kind_names.get(stats["chosen_kind"]),
+                "exchange": it.exchange, "parallelism": f"row-sharded x{world} (merge-path nnz split)",
+                "l2": "inputs larger than L2 (no flush needed)" if alg_bytes_total > 4 * 126e6
+                      else "inputs smaller than L2: steps run back to back, L2-warm",
+                "generation_s": t_gen, "eigen_estimate": eig,
+                "row_stats": {k: stats[k] for k in ("max_row_len", "mean_row_len", "std_row_len", "empty_rows")},
+            },
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                         "peak_source": peak_src, "kernel_ms": kern_ms,
+                         "kernel": f"{kind_names.get(stats['chosen_kind'])} main kernel, rank 0 shard",
+                         "algorithmic_bytes_per_launch": alg_bytes_local,
+                         "kernel_share_of_step": kern_ms / (elapsed_ms / args.steps),
+                         "frac_of_datasheet_8000": (achieved / 8000.0) if achieved else None},
+            "cpu_baseline": cpu_info,
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def C_double():
+    import ctypes
+    return ctypes.c_double(0.0)
+
+
+def C_int64():
+    import ctypes
+    return ctypes.c_int64(0)
+
+
+def main():
+    args = parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        return reference_arm(args, rank, world)
+    from spmv_samples_b200.dist import init_distributed
+    rank, world, local_rank = init_distributed()
+    if world != args.gpus and rank == 0:
+        print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+    return own_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

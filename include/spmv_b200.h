@@ -175,6 +175,11 @@ SPMVB200_API int spmvb200_matrix_create(int offset_bits, int value_bits, int64_t
                                         int64_t n_cols, int64_t nnz, const void *Ap_host,
                                         const int32_t *Aj_host, const void *Ax_host,
                                         spmvb200_matrix_t **out);
+/* Same object over CSR arrays that already live on the device (borrowed, never freed). */
+SPMVB200_API int spmvb200_matrix_create_from_device(int offset_bits, int value_bits, int64_t n_rows,
+                                                    int64_t n_cols, int64_t nnz, const void *Ap_dev,
+                                                    const int32_t *Aj_dev, const void *Ax_dev,
+                                                    spmvb200_matrix_t **out);
 SPMVB200_API int spmvb200_matrix_spmv_host(spmvb200_matrix_t *m, int kind, const void *x_host,
                                            void *y_host);
 SPMVB200_API void spmvb200_matrix_destroy(spmvb200_matrix_t *m);
@@ -201,6 +206,24 @@ SPMVB200_API int spmvb200_gen_rmat_edges(int32_t scale, uint64_t seed, uint64_t 
 SPMVB200_API int spmvb200_coo_to_csr(int offset_bits, int value_bits, int32_t n_rows, int64_t nnz,
                                      int32_t *rows, int32_t *cols, const void *vals, void *Ap,
                                      int32_t *Aj, void *Ax, spmvb200_stream_t stream);
+
+/* ---- power iteration helpers (the row-sharded iterated SpMV of BASELINE.json configs[4]) --
+ * sumsq_dev (DEVICE, one double) = sum of v[i]^2, deterministic two-pass reduction;
+ * alpha_dev (DEVICE, one value-typed scalar) = 1 / sqrt(*sumsq_dev), or 1 if the sum is 0. */
+SPMVB200_API int spmvb200_sum_squares(int value_bits, int64_t n, const void *v, double *sumsq_dev,
+                                      spmvb200_stream_t stream);
+SPMVB200_API int spmvb200_inv_sqrt(int value_bits, const double *sumsq_dev, void *alpha_dev,
+                                   spmvb200_stream_t stream);
+
+/* ---- device timing of the dominant kernel (bench.py's roofline.achieved) ------------------
+ * With option "time_main_kernel" = 1 every merge / vector / light call brackets its main
+ * kernel with cudaEvents on the caller's stream.  This call synchronises on them, returns the
+ * summed milliseconds and the number of launches since the last call, and resets both. */
+SPMVB200_API int spmvb200_main_kernel_time(double *total_ms, int64_t *launches);
+
+/* ---- plain device memory (cudaMalloc), exportable with spmvb200_ipc_export ---------------- */
+SPMVB200_API int spmvb200_device_malloc(size_t bytes, void **dev_ptr);
+SPMVB200_API int spmvb200_device_free(void *dev_ptr);
 
 /* ---- peer mapping for the fused SpMV + all-gather (one process per GPU) ---------------- */
 #define SPMVB200_IPC_HANDLE_BYTES 64

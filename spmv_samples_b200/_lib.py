@@ -102,6 +102,12 @@ def lib() -> C.CDLL:
     L.spmvb200_matrix_create.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64,
                                          C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.POINTER(C.c_void_p)]
+    L.spmvb200_matrix_create_from_device.argtypes = L.spmvb200_matrix_create.argtypes
+    L.spmvb200_sum_squares.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.spmvb200_inv_sqrt.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.spmvb200_main_kernel_time.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    L.spmvb200_device_malloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+    L.spmvb200_device_free.argtypes = [C.c_void_p]
     L.spmvb200_matrix_spmv_host.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.spmvb200_matrix_destroy.argtypes = [C.c_void_p]
     L.spmvb200_matrix_destroy.restype = None

@@ -200,7 +200,77 @@ struct spmvb200_matrix {
     void *Ap = nullptr, *Ax = nullptr, *x = nullptr, *y = nullptr;
     int32_t *Aj = nullptr;
     cudaStream_t stream = nullptr;
+    bool owns_csr = true;
 };
+
+namespace spmvb200 {
+template <typename ValT> int sum_squares(int64_t, const ValT *, double *, cudaStream_t);
+template <typename ValT> int inv_sqrt(const double *, ValT *, cudaStream_t);
+}  // namespace spmvb200
+
+extern "C" {
+
+int spmvb200_sum_squares(int value_bits, int64_t n, const void *v, double *sumsq_dev,
+                         spmvb200_stream_t stream) {
+    if (n < 0 || !sumsq_dev || (n > 0 && !v)) return SPMVB200_ERR_INVALID;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (value_bits == 32) return sum_squares<float>(n, static_cast<const float *>(v), sumsq_dev, s);
+    if (value_bits == 64) return sum_squares<double>(n, static_cast<const double *>(v), sumsq_dev, s);
+    return SPMVB200_ERR_UNSUPPORTED;
+}
+int spmvb200_inv_sqrt(int value_bits, const double *sumsq_dev, void *alpha_dev, spmvb200_stream_t stream) {
+    if (!sumsq_dev || !alpha_dev) return SPMVB200_ERR_INVALID;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (value_bits == 32) return inv_sqrt<float>(sumsq_dev, static_cast<float *>(alpha_dev), s);
+    if (value_bits == 64) return inv_sqrt<double>(sumsq_dev, static_cast<double *>(alpha_dev), s);
+    return SPMVB200_ERR_UNSUPPORTED;
+}
+int spmvb200_main_kernel_time(double *total_ms, int64_t *launches) {
+    if (!total_ms || !launches) return SPMVB200_ERR_INVALID;
+    kernel_timer_read(total_ms, launches);
+    return SPMVB200_OK;
+}
+int spmvb200_device_malloc(size_t bytes, void **dev_ptr) {
+    if (!dev_ptr) return SPMVB200_ERR_INVALID;
+    SPMV_CUDA_TRY(cudaMalloc(dev_ptr, bytes ? bytes : 16));
+    return SPMVB200_OK;
+}
+int spmvb200_device_free(void *dev_ptr) {
+    if (dev_ptr) SPMV_CUDA_TRY(cudaFree(dev_ptr));
+    return SPMVB200_OK;
+}
+int spmvb200_matrix_create_from_device(int offset_bits, int value_bits, int64_t n_rows, int64_t n_cols,
+                                       int64_t nnz, const void *Ap_dev, const int32_t *Aj_dev,
+                                       const void *Ax_dev, spmvb200_matrix_t **out) {
+    if (!out || n_rows < 0 || n_cols < 0 || nnz < 0) return SPMVB200_ERR_INVALID;
+    if ((offset_bits != 32 && offset_bits != 64) || (value_bits != 32 && value_bits != 64))
+        return SPMVB200_ERR_UNSUPPORTED;
+    if (!Ap_dev || (nnz > 0 && (!Aj_dev || !Ax_dev))) return SPMVB200_ERR_INVALID;
+    spmvb200_matrix *m = new (std::nothrow) spmvb200_matrix;
+    if (!m) return SPMVB200_ERR_INVALID;
+    m->offset_bits = offset_bits;
+    m->value_bits = value_bits;
+    m->n_rows = n_rows;
+    m->n_cols = n_cols;
+    m->nnz = nnz;
+    m->owns_csr = false;
+    m->Ap = const_cast<void *>(Ap_dev);
+    m->Aj = const_cast<int32_t *>(Aj_dev);
+    m->Ax = const_cast<void *>(Ax_dev);
+    const size_t vb = value_bits / 8;
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaMalloc(&m->x, (size_t)(n_cols ? n_cols : 1) * vb)) != cudaSuccess ||
+        (e = cudaMalloc(&m->y, (size_t)(n_rows ? n_rows : 1) * vb)) != cudaSuccess) {
+        record_cuda_error(e, "matrix_create_from_device", __FILE__, __LINE__);
+        spmvb200_matrix_destroy(m);
+        return SPMVB200_ERR_CUDA;
+    }
+    *out = m;
+    return SPMVB200_OK;
+}
+
+}  // extern "C"
 
 extern "C" {
 
@@ -272,9 +342,11 @@ int spmvb200_matrix_spmv_host(spmvb200_matrix_t *m, int kind, const void *x_host
 void spmvb200_matrix_destroy(spmvb200_matrix_t *m) {
     if (!m) return;
     if (m->stream) cudaStreamSynchronize(m->stream);
-    if (m->Ap) cudaFree(m->Ap);
-    if (m->Aj) cudaFree(m->Aj);
-    if (m->Ax) cudaFree(m->Ax);
+    if (m->owns_csr) {
+        if (m->Ap) cudaFree(m->Ap);
+        if (m->Aj) cudaFree(m->Aj);
+        if (m->Ax) cudaFree(m->Ax);
+    }
     if (m->x) cudaFree(m->x);
     if (m->y) cudaFree(m->y);
     if (m->stream) cudaStreamDestroy(m->stream);

@@ -60,6 +60,21 @@ void scratch_release_all();
 
 int64_t option_get(const char *name, int64_t fallback);
 
+// cudaEvent bracket around the dominant kernel of a call (no-op unless "time_main_kernel")
+class KernelTimerScope {
+public:
+    explicit KernelTimerScope(cudaStream_t s);
+    ~KernelTimerScope();
+    KernelTimerScope(const KernelTimerScope &) = delete;
+    KernelTimerScope &operator=(const KernelTimerScope &) = delete;
+
+private:
+    cudaStream_t stream_;
+    cudaEvent_t a_ = nullptr, b_ = nullptr;
+    bool active_ = false;
+};
+void kernel_timer_read(double *total_ms, int64_t *launches);
+
 // Extra destinations of every y store (peer GPUs' replicas of the next x).
 constexpr int kMaxPeers = 8;
 struct PeerOut {

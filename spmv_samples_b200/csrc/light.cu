@@ -87,9 +87,12 @@ int launch_T(const SpmvProblem<OffT, ValT> &p, int rows_per_claim) {
     LaunchCfg lc;
     make_launch_cfg(lc, dim3((unsigned)blocks), dim3(kLightBlock), 0, p.stream, p.x,
                     (size_t)p.n_cols * sizeof(ValT));
-    SPMV_CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, light_kernel<T, OffT, ValT>, p.n_rows, p.nnz, p.Ap,
-                                     p.Aj, p.Ax, p.x, p.y, p.alpha_dev, p.peers,
-                                     static_cast<unsigned long long *>(counter), rows_per_claim));
+    {
+        KernelTimerScope timed(p.stream);
+        SPMV_CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, light_kernel<T, OffT, ValT>, p.n_rows, p.nnz, p.Ap,
+                                         p.Aj, p.Ax, p.x, p.y, p.alpha_dev, p.peers,
+                                         static_cast<unsigned long long *>(counter), rows_per_claim));
+    }
     SPMV_LAUNCH_CHECK();
     return SPMVB200_OK;
 }

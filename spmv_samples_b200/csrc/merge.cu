@@ -329,25 +329,30 @@ int launch_merge(const SpmvProblem<OffT, ValT> &p) {
     SPMV_TRY(launch_partition<OffT>(p.n_rows, p.nnz, p.Ap, kMergeTile, num_tiles + 1,
                                     static_cast<int32_t *>(coords), p.stream));
 
-    static bool attr_set = false;  // per instantiation
+    static int64_t attr_carveout = -2;  // per instantiation: last carveout applied
     constexpr size_t smem = merge_smem_bytes<OffT, ValT>();
-    if (!attr_set) {
+    // Shared-memory carveout in percent of the unified L1/shared array.  The x gathers need
+    // the L1 side: all-shared (100) measured 1.8x slower on R-MAT than the driver's default
+    // (2435 vs 1355 us on c3), so the split is a tunable ("merge_carveout", -1 = default).
+    const int64_t carveout = option_get("merge_carveout", -1);
+    if (attr_carveout != carveout) {
         SPMV_CUDA_TRY(cudaFuncSetAttribute(merge_tile_kernel<OffT, ValT>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        // the whole unified array as shared memory: without this the driver's carveout left
-        // room for 6 CTAs/SM (ncu launch__occupancy_limit_shared_mem), the kernel wants 8
         SPMV_CUDA_TRY(cudaFuncSetAttribute(merge_tile_kernel<OffT, ValT>,
                                            cudaFuncAttributePreferredSharedMemoryCarveout,
-                                           (int)cudaSharedmemCarveoutMaxShared));
-        attr_set = true;
+                                           carveout < 0 ? (int)cudaSharedmemCarveoutDefault : (int)carveout));
+        attr_carveout = carveout;
     }
     LaunchCfg lc;
     make_launch_cfg(lc, dim3((unsigned)num_tiles), dim3(kMergeBlock), smem, p.stream, p.x,
                     (size_t)p.n_cols * sizeof(ValT));
-    SPMV_CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, merge_tile_kernel<OffT, ValT>, p.n_rows, p.nnz, p.Ap,
-                                     p.Aj, p.Ax, p.x, p.y, p.alpha_dev, p.peers,
-                                     (const int32_t *)coords, static_cast<int32_t *>(crow),
-                                     static_cast<ValT *>(cval)));
+    {
+        KernelTimerScope timed(p.stream);
+        SPMV_CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, merge_tile_kernel<OffT, ValT>, p.n_rows, p.nnz,
+                                         p.Ap, p.Aj, p.Ax, p.x, p.y, p.alpha_dev, p.peers,
+                                         (const int32_t *)coords, static_cast<int32_t *>(crow),
+                                         static_cast<ValT *>(cval)));
+    }
     SPMV_LAUNCH_CHECK();
 
     if (num_tiles > 1) {

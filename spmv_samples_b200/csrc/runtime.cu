@@ -38,6 +38,8 @@ std::map<std::string, int64_t> &options() {
         {"vector_width", 0},     // 0: from row statistics; else force lanes per row (1..32)
         {"light_width", 0},      // same for the dynamic-row kernel
         {"light_rows_per_claim", 0},  // 0: automatic
+        {"time_main_kernel", 0}, // 1: cudaEvent bracket around each call's dominant kernel
+        {"merge_carveout", -1},  // shared-memory carveout (percent) of the merge tile kernel
         {"auto_kind", -1},       // -1: selector decides; else force a SPMVB200_KIND_*
         {"cusparse_preprocess", 0},  // 1: run cusparseSpMV_preprocess when a plan is built.  Only
                                      // safe while the matrix contents behind (Ap, Aj, Ax) do not
@@ -128,6 +130,59 @@ int option_set(const char *name, int64_t v) {
     if (it == options().end()) return SPMVB200_ERR_INVALID;
     it->second = v;
     return SPMVB200_OK;
+}
+
+// ---- cudaEvent bracket around the dominant kernel (option "time_main_kernel") -----------
+namespace {
+struct EventPair {
+    cudaEvent_t a, b;
+};
+std::vector<EventPair> g_ev_free, g_ev_pending;
+double g_ev_ms = 0.0;
+int64_t g_ev_count = 0;
+
+void fold_pending_locked() {
+    for (auto &p : g_ev_pending) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            g_ev_ms += ms;
+            ++g_ev_count;
+        }
+        g_ev_free.push_back(p);
+    }
+    g_ev_pending.clear();
+}
+}  // namespace
+
+KernelTimerScope::KernelTimerScope(cudaStream_t s) : stream_(s) {
+    if (option_get("time_main_kernel", 0) <= 0) return;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_ev_pending.size() >= 2048) fold_pending_locked();
+    EventPair p;
+    if (!g_ev_free.empty()) {
+        p = g_ev_free.back();
+        g_ev_free.pop_back();
+    } else if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) {
+        return;
+    }
+    a_ = p.a;
+    b_ = p.b;
+    active_ = true;
+    cudaEventRecord(a_, stream_);
+}
+KernelTimerScope::~KernelTimerScope() {
+    if (!active_) return;
+    cudaEventRecord(b_, stream_);
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_ev_pending.push_back(EventPair{a_, b_});
+}
+void kernel_timer_read(double *total_ms, int64_t *launches) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    fold_pending_locked();
+    *total_ms = g_ev_ms;
+    *launches = g_ev_count;
+    g_ev_ms = 0.0;
+    g_ev_count = 0;
 }
 
 void make_launch_cfg(LaunchCfg &lc, dim3 grid, dim3 block, size_t smem, cudaStream_t stream,

@@ -53,8 +53,11 @@ int launch_T(const SpmvProblem<OffT, ValT> &p) {
     LaunchCfg lc;
     make_launch_cfg(lc, dim3((unsigned)blocks), dim3(kVecBlock), 0, p.stream, p.x,
                     (size_t)p.n_cols * sizeof(ValT));
-    SPMV_CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, vector_kernel<T, OffT, ValT>, p.n_rows, p.nnz, p.Ap,
-                                     p.Aj, p.Ax, p.x, p.y, p.alpha_dev, p.peers));
+    {
+        KernelTimerScope timed(p.stream);
+        SPMV_CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, vector_kernel<T, OffT, ValT>, p.n_rows, p.nnz,
+                                         p.Ap, p.Aj, p.Ax, p.x, p.y, p.alpha_dev, p.peers));
+    }
     SPMV_LAUNCH_CHECK();
     return SPMVB200_OK;
 }

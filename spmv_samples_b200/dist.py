@@ -1,0 +1,243 @@
+"""Row-sharded iterated SpMV (power iteration) over the GPUs of one box: one process per GPU.
+
+New with respect to the reference, which is single-device; specified by
+BASELINE.json: rows are split by nnz-balanced merge-path boundaries (the same device search
+that cuts tiles), every rank keeps its rows of A and a full replica of x, and after each
+SpMV every rank needs everybody's slice of the new x.
+
+Two exchanges:
+
+  "p2p"   the SpMV kernel itself stores each y value into the local replica AND into the
+          peer-mapped replicas of the other GPUs (cudaIpc handles over NVLink / NVSwitch), so
+          the all-gather is fused into the kernel's epilogue and overlaps its own gathers; the
+          only collective left is the 8-byte all-reduce of the squared norm, which doubles as
+          the step barrier.
+  "nccl"  the kernel stores locally, then an NCCL all-gather of the (uneven) slices.
+
+x is double-buffered: step t reads buffer t % 2 and writes buffer (t + 1) % 2; a rank cannot
+start step t + 1 before the norm all-reduce of step t, which every rank enters after its own
+step-t kernel has finished reading and writing, so one collective per step orders everything.
+
+The power iteration is x <- A x / ||A x||; the 1/||.|| is applied by the next SpMV through its
+device-side alpha, so the host never synchronises inside the loop.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib, generate, spmv as spmv_mod
+
+
+class _RawDeviceArray:
+    """A cudaMalloc'ed buffer exposed to torch without copying (__cuda_array_interface__)."""
+
+    def __init__(self, n: int, dtype: torch.dtype):
+        self.n = n
+        self.dtype = dtype
+        self.itemsize = torch.empty(0, dtype=dtype).element_size()
+        p = C.c_void_p()
+        _lib.check(_lib.lib().spmvb200_device_malloc(max(n, 1) * self.itemsize, C.byref(p)),
+                   "spmvb200_device_malloc")
+        self.ptr = p.value
+        typestr = {torch.float32: "<f4", torch.float64: "<f8"}[dtype]
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (self.ptr, False),
+                                         "version": 2, "strides": None}
+
+    def tensor(self) -> torch.Tensor:
+        return torch.as_tensor(self, device=f"cuda:{torch.cuda.current_device()}")
+
+    def ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+        _lib.check(_lib.lib().spmvb200_ipc_export(C.c_void_p(self.ptr), buf), "spmvb200_ipc_export")
+        return buf.raw
+
+    def free(self):
+        if self.ptr:
+            _lib.lib().spmvb200_device_free(C.c_void_p(self.ptr))
+            self.ptr = 0
+
+
+def _ipc_open(handle: bytes) -> int:
+    p = C.c_void_p()
+    _lib.check(_lib.lib().spmvb200_ipc_open(handle, C.byref(p)), "spmvb200_ipc_open")
+    return p.value
+
+
+@dataclass
+class Shard:
+    rank: int
+    world: int
+    row_begin: int
+    row_end: int
+    nnz_begin: int
+    nnz_end: int
+    row_bounds: list
+    csr: generate.Csr  # local rows, offsets rebased to 0, n_cols = global
+
+
+def shard_rows(global_csr: generate.Csr, rank: int, world: int, value_seed=None) -> Shard:
+    """Cut rank's rows out of a global CSR held on this device.  Boundaries come from the
+    device merge-path search (bit-exact against oracle.cpu.row_split in the tests)."""
+    rb = spmv_mod.row_split(global_csr.Ap, world, nnz=global_csr.nnz) if world > 1 else \
+        [0, global_csr.n_rows]
+    r0, r1 = rb[rank], rb[rank + 1]
+    k0, k1 = int(global_csr.Ap[r0].item()), int(global_csr.Ap[r1].item())
+    if world == 1:
+        local = global_csr
+    else:
+        Ap = (global_csr.Ap[r0:r1 + 1] - k0).contiguous()
+        Aj = global_csr.Aj[k0:k1].clone()
+        Ax = global_csr.Ax[k0:k1].clone()
+        local = generate.Csr(r1 - r0, global_csr.n_cols, k1 - k0, Ap, Aj, Ax,
+                             f"{global_csr.name}[rank {rank}/{world}]")
+    return Shard(rank, world, r0, r1, k0, k1, rb, local)
+
+
+class PowerIteration:
+    """x <- A x / ||A x||, A row-sharded over `world` ranks (world = 1: the whole matrix)."""
+
+    def __init__(self, shard: Shard, n_rows_global: int, kind: str = "auto", exchange: str = "p2p",
+                 group=None, host_ops=None):
+        """host_ops: TEST HOOK ONLY -- an object with spmv(csr, x, y, alpha) for CPU tensors, so
+        the exchange protocol (double buffering, uneven all-gather, norm all-reduce) can be
+        exercised with the gloo backend where there is no GPU.  The product never passes it;
+        without it every step goes through libspmvb200 and needs CUDA."""
+        import torch.distributed as dist
+        self.dist = dist
+        self.host_ops = host_ops
+        self.shard = shard
+        self.world, self.rank = shard.world, shard.rank
+        self.kind = kind
+        self.n = n_rows_global
+        self.group = group
+        m = shard.csr
+        self.dtype = m.Ax.dtype
+        self.vbits = m.Ax.element_size() * 8
+        assert m.n_cols == n_rows_global, "power iteration needs a square matrix"
+        if host_ops is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError("PowerIteration needs a CUDA device; there is no CPU path")
+            self._raw = [_RawDeviceArray(self.n, self.dtype) for _ in range(2)]
+            self.xbuf = [r.tensor() for r in self._raw]
+            dev = "cuda"
+        else:
+            self._raw = []
+            self.xbuf = [torch.zeros(self.n, dtype=self.dtype) for _ in range(2)]
+            dev = "cpu"
+            if exchange == "p2p":
+                exchange = "nccl"  # collectives only on the host
+        self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.alpha = torch.ones(1, dtype=self.dtype, device=dev)
+        self.step_no = 0
+        self.exchange = exchange if self.world > 1 else "none"
+        self.peer_ptrs = [[], []]  # per buffer: peers' base addresses (mapped into this process)
+        if self.exchange == "p2p":
+            try:
+                self._map_peers()
+            except Exception as e:  # no IPC / no peer access: fall back to NCCL, and say so
+                self.exchange = "nccl"
+                self.exchange_note = f"p2p unavailable ({e}); nccl all-gather"
+        self.reset()
+
+    # ------------------------------------------------------------------ setup
+    def _map_peers(self):
+        handles = [r.ipc_handle() for r in self._raw]
+        gathered = [None] * self.world
+        self.dist.all_gather_object(gathered, handles, group=self.group)
+        for q in range(self.world):
+            if q == self.rank:
+                continue
+            for b in range(2):
+                self.peer_ptrs[b].append(_ipc_open(gathered[q][b]))
+        # every rank must have every mapping before anybody stores through one
+        self.dist.barrier(group=self.group)
+
+    def reset(self):
+        """x0 = 1/sqrt(n), alpha = 1."""
+        self.xbuf[0].fill_(1.0 / (self.n ** 0.5))
+        self.xbuf[1].zero_()
+        self.alpha.fill_(1.0)
+        self.step_no = 0
+        if self.host_ops is None:
+            torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier(group=self.group)
+
+    # ------------------------------------------------------------------ one step
+    def step(self):
+        s, m = self.shard, self.shard.csr
+        cur, nxt = self.step_no & 1, (self.step_no + 1) & 1
+        x = self.xbuf[cur]
+        y = self.xbuf[nxt][s.row_begin:s.row_end]
+        item = self.xbuf[nxt].element_size()
+        peers = [p + s.row_begin * item for p in self.peer_ptrs[nxt]] if self.exchange == "p2p" else []
+        if self.host_ops is None:
+            spmv_mod.spmv_ex(self.kind, m.Ap, m.Aj, m.Ax, x, y, n_cols=self.n, alpha_dev=self.alpha,
+                             y_peers=peers)
+            L = _lib.lib()
+            st = L.spmvb200_sum_squares(self.vbits, y.numel(), y.data_ptr(), self.sumsq.data_ptr(),
+                                        torch.cuda.current_stream().cuda_stream)
+            _lib.check(st, "spmvb200_sum_squares")
+        else:
+            self.host_ops.spmv(m, x, y, self.alpha)
+            self.sumsq[0] = (y.double() ** 2).sum()
+        if self.world > 1:
+            if self.exchange == "nccl":
+                views = [self.xbuf[nxt][s.row_bounds[q]:s.row_bounds[q + 1]] for q in range(self.world)]
+                even = len({v.numel() for v in views}) == 1
+                if even or self.dist.get_backend(self.group) == "nccl":
+                    self.dist.all_gather(views, y, group=self.group)   # NCCL takes uneven slices
+                else:
+                    for q in range(self.world):                        # gloo: one broadcast per slice
+                        self.dist.broadcast(views[q], src=q, group=self.group)
+            # the norm all-reduce is also the step barrier for the peer stores
+            self.dist.all_reduce(self.sumsq, group=self.group)
+        if self.host_ops is None:
+            st = L.spmvb200_inv_sqrt(self.vbits, self.sumsq.data_ptr(), self.alpha.data_ptr(),
+                                     torch.cuda.current_stream().cuda_stream)
+            _lib.check(st, "spmvb200_inv_sqrt")
+        else:
+            s2 = float(self.sumsq[0])
+            self.alpha[0] = 1.0 / (s2 ** 0.5) if s2 > 0 else 1.0
+        self.step_no += 1
+
+    def current_x(self) -> torch.Tensor:
+        """The latest iterate, not yet scaled by alpha (= 1 / its norm)."""
+        return self.xbuf[self.step_no & 1]
+
+    def eigen_estimate(self) -> float:
+        """||A x_k|| with ||x_k|| = 1: converges to |lambda_max|."""
+        return float(self.sumsq.item()) ** 0.5
+
+    def close(self):
+        if self.host_ops is None:
+            torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier(group=self.group)
+        for b in range(2):
+            for p in self.peer_ptrs[b]:
+                _lib.lib().spmvb200_ipc_close(C.c_void_p(p))
+        self.peer_ptrs = [[], []]
+        self.xbuf = []
+        for r in self._raw:
+            r.free()
+
+
+def init_distributed():
+    """(rank, world, local_rank) from torchrun's environment; NCCL over NVLink when world > 1."""
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local_rank)
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {"device_id": torch.device("cuda", local_rank)} if backend == "nccl" else {}
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
+    return rank, world, local_rank

@@ -37,6 +37,22 @@ class CsrMatrix:
         _lib.check(st, "spmvb200_matrix_create")
         self._h = h
 
+    @classmethod
+    def from_device(cls, csr) -> "CsrMatrix":
+        """Wrap CSR arrays that already live on the device (a generate.Csr); they are borrowed,
+        not copied, and must outlive the object."""
+        self = cls.__new__(cls)
+        self.n_rows, self.n_cols, self.nnz = int(csr.n_rows), int(csr.n_cols), int(csr.nnz)
+        self.dtype = np.dtype(np.float32 if csr.Ax.element_size() == 4 else np.float64)
+        self._keep = csr
+        h = C.c_void_p()
+        st = _lib.lib().spmvb200_matrix_create_from_device(
+            csr.Ap.element_size() * 8, csr.Ax.element_size() * 8, self.n_rows, self.n_cols,
+            self.nnz, csr.Ap.data_ptr(), csr.Aj.data_ptr(), csr.Ax.data_ptr(), C.byref(h))
+        _lib.check(st, "spmvb200_matrix_create_from_device")
+        self._h = h
+        return self
+
     def spmv(self, x: np.ndarray, y: np.ndarray | None = None, kind: str = "auto") -> np.ndarray:
         """y = A @ x, host in / host out (pinned or pageable)."""
         if kind not in KIND_IDS:

@@ -1,0 +1,102 @@
+"""CPU suite, world_size 2 over gloo: the exchange protocol of the row-sharded power iteration
+(spmv_samples_b200/dist.py) -- nnz-balanced row split, double-buffered x, uneven all-gather,
+norm all-reduce as the step barrier, lagged device-style alpha -- gives the same iterates as
+the single-process iteration.  The SpMV itself is stubbed with the CPU oracle through the
+documented test hook (host_ops); the CUDA kernels are covered by the -m gpu suite."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import cpu, generators as g
+from spmv_samples_b200 import generate
+from spmv_samples_b200.dist import PowerIteration, Shard
+
+
+class OracleOps:
+    """y = alpha * A_local x with the CPU oracle (cpu_navie.hpp:3-17)."""
+
+    def spmv(self, csr, x, y, alpha):
+        out = cpu.spmv(csr.Ap.numpy(), csr.Aj.numpy(), csr.Ax.numpy(), x.numpy())
+        y.copy_(torch.from_numpy(out * np.float32(alpha.item())))
+
+
+def make_shard(Ap, Aj, Ax, rank, world):
+    n = Ap.shape[0] - 1
+    rb = cpu.row_split(Ap, world).tolist() if world > 1 else [0, n]
+    r0, r1 = rb[rank], rb[rank + 1]
+    k0, k1 = int(Ap[r0]), int(Ap[r1])
+    local = generate.Csr(r1 - r0, n, k1 - k0, torch.from_numpy((Ap[r0:r1 + 1] - k0).copy()),
+                         torch.from_numpy(Aj[k0:k1].copy()), torch.from_numpy(Ax[k0:k1].copy()), "t")
+    return Shard(rank, world, r0, r1, k0, k1, rb, local)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, steps, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    Ap, Aj, Ax = g.rmat(10, 16, 7)
+    shard = make_shard(Ap, Aj, Ax, rank, world)
+    it = PowerIteration(shard, Ap.shape[0] - 1, exchange="nccl", host_ops=OracleOps())
+    assert it.exchange == "nccl"
+    for _ in range(steps):
+        it.step()
+    np.save(os.path.join(out_dir, f"x_{rank}.npy"), it.current_x().numpy())
+    np.save(os.path.join(out_dir, f"s_{rank}.npy"), it.sumsq.numpy())
+    it.close()
+    dist.destroy_process_group()
+
+
+def test_two_rank_power_iteration_matches_single_process(tmp_path):
+    steps = 6
+    mp.spawn(_worker, args=(2, _free_port(), steps, str(tmp_path)), nprocs=2, join=True)
+    x0 = np.load(tmp_path / "x_0.npy")
+    x1 = np.load(tmp_path / "x_1.npy")
+    assert np.array_equal(x0, x1)                      # both replicas hold the same iterate
+    assert np.array_equal(np.load(tmp_path / "s_0.npy"), np.load(tmp_path / "s_1.npy"))
+    # single process, same arithmetic: y = alpha * (A x), alpha = 1/||y_prev||
+    Ap, Aj, Ax = g.rmat(10, 16, 7)
+    n = Ap.shape[0] - 1
+    x = np.full(n, 1.0 / np.sqrt(n), dtype=np.float32)
+    alpha = np.float32(1.0)
+    for _ in range(steps):
+        y = cpu.spmv(Ap, Aj, Ax, x) * alpha
+        # the two ranks add their partial sums of squares in rank order
+        rb = cpu.row_split(Ap, 2)
+        ss = sum(float((y[rb[q]:rb[q + 1]].astype(np.float64) ** 2).sum()) for q in range(2))
+        alpha = np.float32(1.0 / np.sqrt(ss))
+        x = y
+    assert np.array_equal(x0, x)
+    assert abs(float(np.load(tmp_path / "s_0.npy")[0]) - ss) <= 1e-12 * ss
+
+
+def test_row_split_is_nnz_balanced_and_covers_all_rows():
+    Ap, _, _ = g.rmat(12, 16, 3)
+    n, nnz = Ap.shape[0] - 1, int(Ap[-1])
+    for parts in (2, 4, 8):
+        rb = cpu.row_split(Ap, parts)
+        assert rb[0] == 0 and rb[-1] == n and np.all(np.diff(rb) >= 0)
+        work = np.array([(rb[q + 1] - rb[q]) + (Ap[rb[q + 1]] - Ap[rb[q]]) for q in range(parts)])
+        ideal = (n + nnz) / parts
+        # each shard is within one (longest) row of the ideal share of the merge path
+        assert np.all(np.abs(work - ideal) <= np.diff(Ap).max() + 1)
+
+
+def test_power_iteration_refuses_to_run_without_cuda_or_hook():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    Ap, Aj, Ax = g.rmat(6, 4, 1)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        PowerIteration(make_shard(Ap, Aj, Ax, 0, 1), Ap.shape[0] - 1)

@@ -1,0 +1,156 @@
+"""GPU suite: power-iteration helpers, the single-GPU PowerIteration against the oracle, the
+host-buffer matrix object over device arrays, the dominant-kernel timer, and (when the box has
+at least two GPUs) the two-rank row-sharded iteration with both exchanges."""
+import ctypes as C
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from oracle import cpu, generators as g
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda(built_lib):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_sum_squares_and_inv_sqrt(dt):
+    from spmv_samples_b200 import _lib
+    L = _lib.lib()
+    v = g.gen_x(3, 1_000_003, dt)
+    d = dev(v)
+    ss = torch.zeros(1, dtype=torch.float64, device="cuda")
+    alpha = torch.zeros(1, dtype=d.dtype, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    bits = 32 if dt == np.float32 else 64
+    _lib.check(L.spmvb200_sum_squares(bits, d.numel(), d.data_ptr(), ss.data_ptr(), s), "sumsq")
+    _lib.check(L.spmvb200_inv_sqrt(bits, ss.data_ptr(), alpha.data_ptr(), s), "inv_sqrt")
+    torch.cuda.synchronize()
+    expect = float((v.astype(np.float64) ** 2).sum())
+    assert abs(float(ss.item()) - expect) <= 1e-12 * expect
+    assert abs(float(alpha.item()) - expect ** -0.5) <= 1e-6 * expect ** -0.5
+    # deterministic: same bits every time
+    ss2 = torch.zeros(1, dtype=torch.float64, device="cuda")
+    _lib.check(L.spmvb200_sum_squares(bits, d.numel(), d.data_ptr(), ss2.data_ptr(), s), "sumsq")
+    torch.cuda.synchronize()
+    assert float(ss2.item()) == float(ss.item())
+
+
+@pytest.mark.parametrize("kind", ["merge", "vector", "auto"])
+def test_single_gpu_power_iteration_tracks_the_oracle(kind):
+    from spmv_samples_b200 import generate as gen
+    from spmv_samples_b200.dist import PowerIteration, shard_rows
+    m = gen.rmat(12, 16, 7, offset=torch.int64)
+    Ap, Aj, Ax = g.rmat(12, 16, 7, offset_dtype=np.int64)
+    n = m.n_rows
+    it = PowerIteration(shard_rows(m, 0, 1), n, kind=kind)
+    x = np.full(n, 1.0 / np.sqrt(n), dtype=np.float64)
+    alpha = 1.0
+    for _ in range(8):
+        it.step()
+        y = cpu.spmv_fp64(Ap, Aj, Ax, x.astype(np.float32)) * alpha
+        alpha = 1.0 / np.sqrt((y ** 2).sum())
+        x = y
+    torch.cuda.synchronize()
+    got = it.current_x().cpu().numpy().astype(np.float64)
+    # fp32 iterates drift from the fp64 recurrence by rounding only
+    assert np.linalg.norm(got - x) <= 1e-4 * np.linalg.norm(x)
+    assert abs(it.eigen_estimate() - np.sqrt((x ** 2).sum())) <= 1e-4 * np.sqrt((x ** 2).sum())
+    it.close()
+
+
+def test_matrix_object_over_device_arrays():
+    from spmv_samples_b200 import generate as gen
+    from spmv_samples_b200.matrix import CsrMatrix
+    m = gen.uniform_rows(5000, 5000, 8, 4)
+    Ap, Aj, Ax = g.uniform_rows(5000, 5000, 8, 4)
+    x = g.gen_x(9, 5000)
+    mat = CsrMatrix.from_device(m)
+    y = mat.spmv(x, kind="auto")
+    y64 = cpu.spmv_fp64(Ap, Aj, Ax, x)
+    assert np.all(np.abs(y - y64) <= 1e-5 * cpu.abs_scale(Ap, Aj, Ax, x))
+    mat.close()
+    assert int(m.Ap[-1]) == m.nnz      # borrowed arrays are still alive
+
+
+def test_dominant_kernel_timer():
+    from spmv_samples_b200 import _lib, generate as gen, spmv
+    m = gen.uniform_rows(200000, 200000, 16, 4)
+    x = gen.gen_x(m.n_cols, 1)
+    y = torch.empty(m.n_rows, device="cuda")
+    ms, cnt = C.c_double(), C.c_int64()
+    spmv.set_option("time_main_kernel", 1)
+    try:
+        _lib.lib().spmvb200_main_kernel_time(C.byref(ms), C.byref(cnt))
+        for kind in ("merge", "vector", "light"):
+            for _ in range(4):
+                spmv.SpMV(kind, m.n_rows, m.n_cols, m.nnz, m.Ap, m.Aj, m.Ax, x, y)
+        _lib.lib().spmvb200_main_kernel_time(C.byref(ms), C.byref(cnt))
+    finally:
+        spmv.set_option("time_main_kernel", 0)
+    assert cnt.value == 12 and 0.0 < ms.value < 1000.0
+    _lib.lib().spmvb200_main_kernel_time(C.byref(ms), C.byref(cnt))
+    assert cnt.value == 0
+
+
+# ------------------------------------------------------------------ two ranks, two GPUs
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _rank_main(rank, world, port, exchange, out_dir):
+    import torch.distributed as dist
+    from spmv_samples_b200 import generate as gen
+    from spmv_samples_b200.dist import PowerIteration, shard_rows
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    m = gen.rmat(14, 16, 7, offset=torch.int64)
+    shard = shard_rows(m, rank, world)
+    it = PowerIteration(shard, m.n_rows, kind="auto", exchange=exchange)
+    for _ in range(6):
+        it.step()
+    torch.cuda.synchronize()
+    np.save(os.path.join(out_dir, f"x_{exchange}_{rank}.npy"), it.current_x().cpu().numpy())
+    open(os.path.join(out_dir, f"ex_{exchange}_{rank}.txt"), "w").write(
+        it.exchange + " " + ",".join(map(str, shard.row_bounds)))
+    it.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+def test_two_gpu_sharded_iteration_matches_single_gpu(tmp_path, exchange):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    from spmv_samples_b200 import generate as gen
+    from spmv_samples_b200.dist import PowerIteration, shard_rows
+    mp.spawn(_rank_main, args=(2, _free_port(), exchange, str(tmp_path)), nprocs=2, join=True)
+    x0 = np.load(tmp_path / f"x_{exchange}_0.npy")
+    x1 = np.load(tmp_path / f"x_{exchange}_1.npy")
+    assert np.array_equal(x0, x1)
+    used, bounds = open(tmp_path / f"ex_{exchange}_0.txt").read().split(" ")
+    Ap, _, _ = g.rmat(14, 16, 7, offset_dtype=np.int64)
+    assert bounds == ",".join(map(str, cpu.row_split(Ap, 2).tolist()))     # bit-exact split
+    m = gen.rmat(14, 16, 7, offset=torch.int64)
+    it = PowerIteration(shard_rows(m, 0, 1), m.n_rows, kind="auto")
+    for _ in range(6):
+        it.step()
+    ref = it.current_x().cpu().numpy()
+    it.close()
+    assert np.linalg.norm(x0.astype(np.float64) - ref) <= 1e-5 * np.linalg.norm(ref)

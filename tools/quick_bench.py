@@ -13,6 +13,8 @@ p.add_argument("--kinds", default="merge,vector,light,auto,cusparse")
 p.add_argument("--iters", type=int, default=20)
 p.add_argument("--opts", default="")  # name=value,name=value
 p.add_argument("--no-flush", action="store_true")
+p.add_argument("--o64", action="store_true")
+p.add_argument("--override", type=int, default=0)
 a = p.parse_args()
 for kv in filter(None, a.opts.split(",")):
     k, v = kv.split("=")
@@ -24,7 +26,9 @@ except Exception:
     pass
 flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
 for cfg in a.configs.split(","):
-    m = gen.make_config(cfg)
+    if a.o64:
+        gen.CONFIGS[cfg]['offset'] = torch.int64
+    m = gen.make_config(cfg, scale_override=a.override or None)
     x = gen.gen_x(m.n_cols, 1, m.Ax.dtype)
     y = torch.empty(m.n_rows, dtype=m.Ax.dtype, device="cuda")
     st = spmv.row_stats(m.Ap, nnz=m.nnz)
