@@ -123,7 +123,7 @@ __device__ __forceinline__ void sts8(double *s, const double (&v)[8]) {
 // ---------------------------------------------------------------------------- tile kernel
 template <typename OffT, typename ValT>
 __global__ void __launch_bounds__(kMergeBlock)
-merge_tile_kernel(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
+merge_tile_tma_kernel(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
                   const int32_t *__restrict__ Aj, const ValT *__restrict__ Ax,
                   const ValT *__restrict__ x, ValT *__restrict__ y,
                   const ValT *__restrict__ alpha_dev, PeerOut peers,
@@ -276,6 +276,177 @@ merge_tile_kernel(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
     }
 }
 
+// ------------------------------------------------------------- tile kernel, register staging
+// The default.  Same tile, same segmented scan, but Aj / Ax go from global memory straight
+// into registers (two 128-bit loads each per thread, 32 contiguous bytes per lane) and the row
+// ends are read by the thread that owns the row, so the only shared memory left is the scan
+// array and the flags: 10 KB (fp32) or 18 KB (fp64) per CTA instead of 27-35 KB.
+// Why it matters: the unified L1/shared array is what holds the lines of the x gathers that
+// are in flight.  With the TMA-staged tile, 6 CTAs took 160-209 KB of it and left 20-68 KB of
+// L1; ncu showed the gather rate tracking that remainder (o64: 35 KB/CTA -> 2.45 ms on R-MAT
+// scale 24, o32: 27 KB/CTA -> 1.32 ms, all-shared carveout -> 2.4 ms), and at scale 27, where
+// every miss is a DRAM round trip, the kernel ran at 7 % of the byte roofline.
+template <typename ValT> struct LoadVals;
+template <> struct LoadVals<float> {
+    static __device__ __forceinline__ void vec8(const float *p, uint64_t pol, float (&v)[8]) {
+        const float4 a = ldg_stream_val4(p, pol), b = ldg_stream_val4(p + 4, pol);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+};
+template <> struct LoadVals<double> {
+    static __device__ __forceinline__ void vec8(const double *p, uint64_t pol, double (&v)[8]) {
+        const double4_t a = ldg_stream_val4(p, pol), b = ldg_stream_val4(p + 4, pol);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+};
+
+template <typename OffT, typename ValT>
+__global__ void __launch_bounds__(kMergeBlock, (sizeof(ValT) == 4 && sizeof(OffT) == 4) ? 8 : (sizeof(ValT) == 4 ? 6 : 4))
+merge_tile_reg_kernel(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
+                      const int32_t *__restrict__ Aj, const ValT *__restrict__ Ax,
+                      const ValT *__restrict__ x, ValT *__restrict__ y,
+                      const ValT *__restrict__ alpha_dev, PeerOut peers,
+                      const int32_t *__restrict__ coords_x, int32_t *__restrict__ carry_row,
+                      ValT *__restrict__ carry_val) {
+    constexpr int IPT = kMergeIPT;
+    __shared__ __align__(16) ValT s_scan[kSlots];
+    __shared__ __align__(16) unsigned char s_flag[kSlots];
+    __shared__ ValT s_wval[kMergeBlock / 32];
+    __shared__ int s_wflag[kMergeBlock / 32];
+
+    const int tid = threadIdx.x;
+    const int64_t tile = blockIdx.x;
+    const int64_t total = (int64_t)n_rows + (int64_t)nnz;
+    const int64_t d0 = tile * kMergeTile;
+    const int64_t d1 = d0 + kMergeTile < total ? d0 + kMergeTile : total;
+    const int32_t sx = __ldg(coords_x + tile);
+    const int32_t ex = __ldg(coords_x + tile + 1);
+    const int64_t sy = d0 - sx;
+    const int R = ex - sx;                // rows that end inside this tile
+    const int Z = (int)((d1 - ex) - sy);  // nonzeros inside this tile
+    const int shift = (int)(sy & 3);      // slot s holds tile-local nonzero s - shift
+    const int64_t a0 = sy - shift;        // 16-byte aligned position of slot 0 in Aj / Ax
+
+    *reinterpret_cast<uint2 *>(s_flag + tid * IPT) = make_uint2(0u, 0u);
+
+    // ---- this thread's 8 consecutive slots straight into registers
+    const int slot0 = tid * IPT;
+    const uint64_t pol_stream = policy_evict_first();
+    const uint64_t pol_x = policy_evict_last();
+    int c[IPT];
+    ValT p[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        c[k] = 0;
+        p[k] = (ValT)0;
+    }
+    if (slot0 < shift + Z) {
+        const int64_t g = a0 + slot0;
+        if (g + IPT <= (int64_t)nnz) {
+            const int4 ca = ldg_stream_int4(Aj + g, pol_stream);
+            const int4 cb = ldg_stream_int4(Aj + g + 4, pol_stream);
+            c[0] = ca.x; c[1] = ca.y; c[2] = ca.z; c[3] = ca.w;
+            c[4] = cb.x; c[5] = cb.y; c[6] = cb.z; c[7] = cb.w;
+            LoadVals<ValT>::vec8(Ax + g, pol_stream, p);
+        } else {  // the last vectors of the matrix: element-wise, inside the arrays
+#pragma unroll
+            for (int k = 0; k < IPT; ++k) {
+                if (g + k < (int64_t)nnz) {
+                    c[k] = __ldg(Aj + g + k);
+                    p[k] = __ldg(Ax + g + k);
+                }
+            }
+        }
+    }
+    const ValT alpha = alpha_dev ? __ldg(alpha_dev) : (ValT)1;
+    __syncthreads();  // flags are clear
+
+    // ---- row-start flags, one thread per row end (Ap read coalesced, no staging)
+    for (int j = tid; j < R; j += kMergeBlock) {
+        const int64_t q = (int64_t)__ldg(Ap + sx + 1 + j) - sy;
+        if (q < Z) s_flag[(int)q + shift] = 1;
+    }
+    // ---- x gathers, all eight issued before the first use
+    {
+        ValT xv[IPT];
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+            const int i = slot0 + k - shift;
+            xv[k] = (i >= 0 && i < Z) ? ldg_hint(x + c[k], pol_x) : (ValT)0;
+        }
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+            const int i = slot0 + k - shift;
+            p[k] = (i >= 0 && i < Z) ? p[k] * xv[k] : (ValT)0;
+        }
+    }
+    __syncthreads();  // flags are set
+
+    // ---- segmented scan (as in the TMA variant)
+    const uint2 fw = *reinterpret_cast<const uint2 *>(s_flag + slot0);
+    const unsigned long long fbits = ((unsigned long long)fw.y << 32) | fw.x;
+    int flag = fbits != 0ull;
+    ValT val = (ValT)0;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) val = ((fbits >> (8 * k)) & 1ull) ? p[k] : val + p[k];
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const ValT pvv = __shfl_up_sync(0xffffffffu, val, d);
+        const int pf = __shfl_up_sync(0xffffffffu, flag, d);
+        if (lane >= d) {
+            if (!flag) val += pvv;
+            flag |= pf;
+        }
+    }
+    if (lane == 31) {
+        s_wval[warp] = val;
+        s_wflag[warp] = flag;
+    }
+    ValT ev = __shfl_up_sync(0xffffffffu, val, 1);
+    int ef = __shfl_up_sync(0xffffffffu, flag, 1);
+    if (lane == 0) {
+        ev = (ValT)0;
+        ef = 0;
+    }
+    __syncthreads();
+    ValT wv = (ValT)0;
+#pragma unroll
+    for (int w = 0; w < kMergeBlock / 32; ++w) {
+        if (w < warp) {
+            const ValT v = s_wval[w];
+            wv = s_wflag[w] ? v : wv + v;
+        }
+    }
+    ValT run = ef ? ev : wv + ev;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        run = ((fbits >> (8 * k)) & 1ull) ? p[k] : run + p[k];
+        p[k] = run;
+    }
+    sts8(s_scan + slot0, p);
+    __syncthreads();
+
+    // ---- one thread per row end: the row's total is the scan value at its last nonzero.
+    // Row sx+j covers tile-local nonzeros [max(Ap[sx+j]-sy, 0), Ap[sx+j+1]-sy).
+    const ValT *scan = s_scan + shift;
+    for (int j = tid; j < R; j += kMergeBlock) {
+        const int64_t b64 = (int64_t)__ldg(Ap + sx + j) - sy;
+        const int q = (int)((int64_t)__ldg(Ap + sx + 1 + j) - sy);
+        const int b = b64 > 0 ? (int)b64 : 0;
+        const ValT sum = q > b ? scan[q - 1] : (ValT)0;
+        store_y(y, peers, (int64_t)sx + j, alpha * sum);
+    }
+    if (tid == 0) {
+        const int64_t lq = R > 0 ? (int64_t)__ldg(Ap + ex) - sy : 0;
+        const int lastq = lq > 0 ? (int)lq : 0;
+        carry_row[tile] = ex;
+        carry_val[tile] = Z > lastq ? scan[Z - 1] : (ValT)0;
+    }
+}
+
 // ------------------------------------------------------------------------- carry fixup
 // One thread per tile.  Consecutive tiles whose carry lands in the same row form a run; the
 // head of the run adds the run's carries, in tile order, to y[row].
@@ -329,26 +500,41 @@ int launch_merge(const SpmvProblem<OffT, ValT> &p) {
     SPMV_TRY(launch_partition<OffT>(p.n_rows, p.nnz, p.Ap, kMergeTile, num_tiles + 1,
                                     static_cast<int32_t *>(coords), p.stream));
 
-    static int64_t attr_carveout = -2;  // per instantiation: last carveout applied
-    constexpr size_t smem = merge_smem_bytes<OffT, ValT>();
-    // Shared-memory carveout in percent of the unified L1/shared array.  The x gathers need
-    // the L1 side: all-shared (100) measured 1.8x slower on R-MAT than the driver's default
-    // (2435 vs 1355 us on c3), so the split is a tunable ("merge_carveout", -1 = default).
+    // "merge_staging": 0 (default) = Aj/Ax into registers, 1 = TMA bulk copies into shared
+    // memory (kept for the ablation that decided against it; see merge_tile_reg_kernel)
+    const bool tma = option_get("merge_staging", 0) == 1;
     const int64_t carveout = option_get("merge_carveout", -1);
-    if (attr_carveout != carveout) {
-        SPMV_CUDA_TRY(cudaFuncSetAttribute(merge_tile_kernel<OffT, ValT>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SPMV_CUDA_TRY(cudaFuncSetAttribute(merge_tile_kernel<OffT, ValT>,
-                                           cudaFuncAttributePreferredSharedMemoryCarveout,
-                                           carveout < 0 ? (int)cudaSharedmemCarveoutDefault : (int)carveout));
-        attr_carveout = carveout;
-    }
     LaunchCfg lc;
-    make_launch_cfg(lc, dim3((unsigned)num_tiles), dim3(kMergeBlock), smem, p.stream, p.x,
-                    (size_t)p.n_cols * sizeof(ValT));
-    {
+    if (tma) {
+        static int64_t attr_carveout = -2;  // per instantiation: last carveout applied
+        constexpr size_t smem = merge_smem_bytes<OffT, ValT>();
+        if (attr_carveout != carveout) {
+            SPMV_CUDA_TRY(cudaFuncSetAttribute(merge_tile_tma_kernel<OffT, ValT>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SPMV_CUDA_TRY(cudaFuncSetAttribute(merge_tile_tma_kernel<OffT, ValT>,
+                                               cudaFuncAttributePreferredSharedMemoryCarveout,
+                                               carveout < 0 ? (int)cudaSharedmemCarveoutDefault : (int)carveout));
+            attr_carveout = carveout;
+        }
+        make_launch_cfg(lc, dim3((unsigned)num_tiles), dim3(kMergeBlock), smem, p.stream, p.x,
+                        (size_t)p.n_cols * sizeof(ValT));
         KernelTimerScope timed(p.stream);
-        SPMV_CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, merge_tile_kernel<OffT, ValT>, p.n_rows, p.nnz,
+        SPMV_CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, merge_tile_tma_kernel<OffT, ValT>, p.n_rows, p.nnz,
+                                         p.Ap, p.Aj, p.Ax, p.x, p.y, p.alpha_dev, p.peers,
+                                         (const int32_t *)coords, static_cast<int32_t *>(crow),
+                                         static_cast<ValT *>(cval)));
+    } else {
+        static int64_t attr_carveout = -2;
+        if (attr_carveout != carveout) {
+            SPMV_CUDA_TRY(cudaFuncSetAttribute(merge_tile_reg_kernel<OffT, ValT>,
+                                               cudaFuncAttributePreferredSharedMemoryCarveout,
+                                               carveout < 0 ? (int)cudaSharedmemCarveoutDefault : (int)carveout));
+            attr_carveout = carveout;
+        }
+        make_launch_cfg(lc, dim3((unsigned)num_tiles), dim3(kMergeBlock), 0, p.stream, p.x,
+                        (size_t)p.n_cols * sizeof(ValT));
+        KernelTimerScope timed(p.stream);
+        SPMV_CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, merge_tile_reg_kernel<OffT, ValT>, p.n_rows, p.nnz,
                                          p.Ap, p.Aj, p.Ax, p.x, p.y, p.alpha_dev, p.peers,
                                          (const int32_t *)coords, static_cast<int32_t *>(crow),
                                          static_cast<ValT *>(cval)));

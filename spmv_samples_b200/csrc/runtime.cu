@@ -40,6 +40,8 @@ std::map<std::string, int64_t> &options() {
         {"light_rows_per_claim", 0},  // 0: automatic
         {"time_main_kernel", 0}, // 1: cudaEvent bracket around each call's dominant kernel
         {"merge_carveout", -1},  // shared-memory carveout (percent) of the merge tile kernel
+        {"l2_fetch_granularity", 0},  // 32/64/128: cudaLimitMaxL2FetchGranularity; 0 = leave
+        {"merge_staging", 0},    // 0: Aj/Ax into registers (default); 1: TMA bulk copies to smem
         {"auto_kind", -1},       // -1: selector decides; else force a SPMVB200_KIND_*
         {"cusparse_preprocess", 0},  // 1: run cusparseSpMV_preprocess when a plan is built.  Only
                                      // safe while the matrix contents behind (Ap, Aj, Ax) do not
@@ -129,6 +131,10 @@ int option_set(const char *name, int64_t v) {
     auto it = options().find(name);
     if (it == options().end()) return SPMVB200_ERR_INVALID;
     it->second = v;
+    // device-wide limit, applied to the current device when the option is set: a random 4-byte
+    // gather that misses L2 only needs one 32-byte sector from HBM, not the default 64 bytes
+    if (std::string(name) == "l2_fetch_granularity" && (v == 32 || v == 64 || v == 128))
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v);
     return SPMVB200_OK;
 }
 

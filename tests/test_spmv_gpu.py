@@ -352,3 +352,32 @@ def test_repeated_calls_are_deterministic():
         y0 = run_kind(kind, Ap, Aj, Ax, x)
         for _ in range(3):
             assert np.array_equal(run_kind(kind, Ap, Aj, Ax, x), y0)
+
+
+@pytest.mark.parametrize("family", sorted(FAMILIES))
+def test_merge_tma_staged_variant_parity(family):
+    """The TMA-bulk-copy staged tile kernel (option merge_staging=1) is kept for the ablation
+    in DESIGN.md; it must stay correct."""
+    from spmv_samples_b200 import spmv
+    Ap, Aj, Ax = FAMILIES[family]()
+    x = g.gen_x(17, int(Aj.max()) + 1, Ax.dtype)
+    spmv.set_option("merge_staging", 1)
+    try:
+        y = run_kind("merge", Ap, Aj, Ax, x)
+    finally:
+        spmv.set_option("merge_staging", 0)
+    assert_within_tolerance(y, Ap, Aj, Ax, x, f"{family}/merge-tma")
+
+
+@pytest.mark.parametrize("case", sorted(EDGE))
+def test_merge_tma_staged_variant_edge_cases(case):
+    from spmv_samples_b200 import spmv
+    Ap, Aj, Ax = EDGE[case]()
+    n_cols = {"n_cols_1": 1}.get(case, int(Aj.max()) + 1 if Aj.size else 10)
+    x = g.gen_x(23, n_cols, Ax.dtype)
+    spmv.set_option("merge_staging", 1)
+    try:
+        y = run_kind("merge", Ap, Aj, Ax, x, n_cols)
+    finally:
+        spmv.set_option("merge_staging", 0)
+    assert_within_tolerance(y, Ap, Aj, Ax, x, f"{case}/merge-tma")

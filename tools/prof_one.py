@@ -9,10 +9,13 @@ p.add_argument("--kind", default="merge")
 p.add_argument("--iters", type=int, default=3)
 p.add_argument("--opts", default="")
 p.add_argument("--override", type=int, default=0)
+p.add_argument("--o64", action="store_true")
 a = p.parse_args()
 for kv in filter(None, a.opts.split(",")):
     k, v = kv.split("=")
     spmv.set_option(k, int(v))
+if a.o64:
+    gen.CONFIGS[a.config]['offset'] = torch.int64
 m = gen.make_config(a.config, scale_override=a.override or None)
 x = gen.gen_x(m.n_cols, 1, m.Ax.dtype)
 y = torch.empty(m.n_rows, dtype=m.Ax.dtype, device="cuda")
