@@ -303,13 +303,13 @@ template <> struct LoadVals<double> {
 };
 
 template <typename OffT, typename ValT>
-__global__ void __launch_bounds__(kMergeBlock, (sizeof(ValT) == 4 && sizeof(OffT) == 4) ? 8 : (sizeof(ValT) == 4 ? 6 : 4))
-merge_tile_reg_kernel(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
-                      const int32_t *__restrict__ Aj, const ValT *__restrict__ Ax,
-                      const ValT *__restrict__ x, ValT *__restrict__ y,
-                      const ValT *__restrict__ alpha_dev, PeerOut peers,
-                      const int32_t *__restrict__ coords_x, int32_t *__restrict__ carry_row,
-                      ValT *__restrict__ carry_val) {
+__device__ __forceinline__ void
+merge_tile_reg_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
+                    const int32_t *__restrict__ Aj, const ValT *__restrict__ Ax,
+                    const ValT *__restrict__ x, ValT *__restrict__ y,
+                    const ValT *__restrict__ alpha_dev, const PeerOut &peers,
+                    const int32_t *__restrict__ coords_x, int32_t *__restrict__ carry_row,
+                    ValT *__restrict__ carry_val) {
     constexpr int IPT = kMergeIPT;
     __shared__ __align__(16) ValT s_scan[kSlots];
     __shared__ __align__(16) unsigned char s_flag[kSlots];
@@ -447,6 +447,27 @@ merge_tile_reg_kernel(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
     }
 }
 
+// Two entry points over one body, because the register budget is set per __global__: with
+// 32-bit offsets and fp32 the body fits 32 registers without spilling (8 CTAs/SM; c3 1328 ->
+// 1230 us); the 64-bit-offset and fp64 bodies spill under that cap and are left to ptxas
+// (40 / 64 registers, 6 / 4 CTAs per SM).
+#define MERGE_REG_KERNEL_ARGS                                                                    \
+    int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap, const int32_t *__restrict__ Aj,       \
+    const ValT *__restrict__ Ax, const ValT *__restrict__ x, ValT *__restrict__ y,               \
+    const ValT *__restrict__ alpha_dev, PeerOut peers, const int32_t *__restrict__ coords_x,     \
+    int32_t *__restrict__ carry_row, ValT *__restrict__ carry_val
+template <typename OffT, typename ValT>
+__global__ void __launch_bounds__(kMergeBlock, 8) merge_tile_reg_kernel_occ8(MERGE_REG_KERNEL_ARGS) {
+    merge_tile_reg_body<OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers, coords_x,
+                                    carry_row, carry_val);
+}
+template <typename OffT, typename ValT>
+__global__ void __launch_bounds__(kMergeBlock) merge_tile_reg_kernel(MERGE_REG_KERNEL_ARGS) {
+    merge_tile_reg_body<OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers, coords_x,
+                                    carry_row, carry_val);
+}
+#undef MERGE_REG_KERNEL_ARGS
+
 // ------------------------------------------------------------------------- carry fixup
 // One thread per tile.  Consecutive tiles whose carry lands in the same row form a run; the
 // head of the run adds the run's carries, in tile order, to y[row].
@@ -524,20 +545,20 @@ int launch_merge(const SpmvProblem<OffT, ValT> &p) {
                                          (const int32_t *)coords, static_cast<int32_t *>(crow),
                                          static_cast<ValT *>(cval)));
     } else {
+        constexpr bool occ8 = sizeof(OffT) == 4 && sizeof(ValT) == 4;
+        auto kernel = occ8 ? merge_tile_reg_kernel_occ8<OffT, ValT> : merge_tile_reg_kernel<OffT, ValT>;
         static int64_t attr_carveout = -2;
         if (attr_carveout != carveout) {
-            SPMV_CUDA_TRY(cudaFuncSetAttribute(merge_tile_reg_kernel<OffT, ValT>,
-                                               cudaFuncAttributePreferredSharedMemoryCarveout,
+            SPMV_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                                carveout < 0 ? (int)cudaSharedmemCarveoutDefault : (int)carveout));
             attr_carveout = carveout;
         }
         make_launch_cfg(lc, dim3((unsigned)num_tiles), dim3(kMergeBlock), 0, p.stream, p.x,
                         (size_t)p.n_cols * sizeof(ValT));
         KernelTimerScope timed(p.stream);
-        SPMV_CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, merge_tile_reg_kernel<OffT, ValT>, p.n_rows, p.nnz,
-                                         p.Ap, p.Aj, p.Ax, p.x, p.y, p.alpha_dev, p.peers,
-                                         (const int32_t *)coords, static_cast<int32_t *>(crow),
-                                         static_cast<ValT *>(cval)));
+        SPMV_CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, kernel, p.n_rows, p.nnz, p.Ap, p.Aj, p.Ax, p.x, p.y,
+                                         p.alpha_dev, p.peers, (const int32_t *)coords,
+                                         static_cast<int32_t *>(crow), static_cast<ValT *>(cval)));
     }
     SPMV_LAUNCH_CHECK();
 
