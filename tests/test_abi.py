@@ -33,8 +33,8 @@ def test_library_is_sm100a_with_tma_bulk_copies(built_lib):
     assert "sm_100a" in r.stdout
     sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True,
                           text=True).stdout
-    assert "merge_tile_kernel" in sass
-    assert "UBLKCP" in sass      # cp.async.bulk staging of the tile segments
+    assert "merge_tile_reg_kernel" in sass and "merge_tile_tma_kernel" in sass
+    assert "UBLKCP" in sass      # cp.async.bulk staging (the TMA-staged ablation variant)
     assert "SYNCS" in sass       # mbarrier completion
     assert re.search(r"LDG\.E\.[A-Z.]*128", sass)   # 128-bit loads of Aj / Ax
 
