@@ -53,7 +53,7 @@ def parse_args():
     p.add_argument("--override", type=int, default=0,
                    help="shrink the workload (R-MAT scale / rows / grid); development only")
     p.add_argument("--kind", default="auto")
-    p.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
+    p.add_argument("--exchange", default="auto", choices=["auto", "mc", "p2p", "nccl"])
     p.add_argument("--e2e-steps", type=int, default=10)
     p.add_argument("--cpu-seconds", type=float, default=15.0,
                    help="budget of the cpu_baseline leg (own arm)")
@@ -341,8 +341,12 @@ def own_arm(args, rank, world, local_rank):
     _lib.lib().spmvb200_main_kernel_time(ctypes.byref(d_ms), ctypes.byref(d_n))
     kern_ms = d_ms.value / max(d_n.value, 1)
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
+    per_rank = torch.zeros(world, 3, dtype=torch.float64, device="cuda")
+    per_rank[rank, 0], per_rank[rank, 1], per_rank[rank, 2] = kern_ms, local.n_rows, local.nnz
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(per_rank)
+    per_rank = per_rank.cpu().tolist()
     elapsed_ms = float(t.item())
     sec = elapsed_ms * 1e-3
     value = 2.0 * nnz_total * args.steps / sec / 1e9
@@ -403,11 +407,13 @@ def own_arm(args, rank, world, local_rank):
                 "step": "one power-iteration SpMV (x <- A x / ||A x||) over the whole matrix, "
                         "incl. x exchange and norm",
                 "kind": args.kind, "selected_kernel": kind_names.get(stats["chosen_kind"]),
-                "exchange": it.exchange, "parallelism": f"row-sharded x{world} (merge-path nnz split)",
+                "exchange": it.exchange, "exchange_note": getattr(it, "exchange_note", ""), "parallelism": f"row-sharded x{world} (merge-path nnz split)",
                 "l2": "inputs larger than L2 (no flush needed)" if alg_bytes_total > 4 * 126e6
                       else "inputs smaller than L2: steps run back to back, L2-warm",
                 "generation_s": t_gen, "eigen_estimate": eig,
                 "row_stats": {k: stats[k] for k in ("max_row_len", "mean_row_len", "std_row_len", "empty_rows")},
+                "per_rank": {"kernel_ms": [round(r[0], 4) for r in per_rank],
+                             "rows": [int(r[1]) for r in per_rank], "nnz": [int(r[2]) for r in per_rank]},
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,

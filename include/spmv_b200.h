@@ -101,7 +101,11 @@ SPMVB200_DECLARE_KIND(cusparse)
  * NULL means 1.  (merge_based/agent_spmv_orig.cuh:425-433 carries alpha the same way.)
  * y_peers / n_peers: optional array (HOST memory) of extra DEVICE pointers that receive the
  * same y stores (peer-mapped buffers of other GPUs; the fused SpMV + all-gather of the
- * row-sharded power iteration).  Each is indexed like y.  Supported by merge/vector/light. */
+ * row-sharded power iteration).  Each is indexed like y.  Supported by merge/vector/light.
+ * Only rows that have nonzeros are stored to the peers (an empty row's y is always 0), so the
+ * peer buffers must hold 0 at the positions of empty rows -- zero them once.
+ * n_peers == -1: y_peers[0] is an NVLink multicast address (NVLS; e.g. the multicast_ptr of a
+ * torch symmetric-memory buffer) and every such row is stored once with multimem.st. */
 typedef struct {
     int32_t kind;
     int32_t offset_bits;

@@ -11,7 +11,7 @@ import os
 import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libspmvb200.so")
+LIB_PATH = os.environ.get("SPMVB200_LIB") or os.path.join(_PKG, "libspmvb200.so")  # env: ablation builds
 CSRC = os.path.join(_PKG, "csrc")
 
 OK = 0

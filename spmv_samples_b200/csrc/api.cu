@@ -41,7 +41,8 @@ int run(int kind, int64_t n_rows, int64_t n_cols, int64_t nnz, const void *Ap, c
     if (n_rows == 0 || n_cols == 0) return SPMVB200_OK;
     if (!Ap || !y || (nnz > 0 && (!Aj || !Ax || !x))) return SPMVB200_ERR_INVALID;
     if (!aligned16(Ap) || !aligned16(Aj) || !aligned16(Ax)) return SPMVB200_ERR_ALIGNMENT;
-    if (n_peers < 0 || n_peers > kMaxPeers || (n_peers > 0 && !y_peers)) return SPMVB200_ERR_INVALID;
+    // n_peers == -1: y_peers[0] is an NVLink multicast address (one store reaches every replica)
+    if (n_peers < -1 || n_peers > kMaxPeers || (n_peers != 0 && (!y_peers || !y_peers[0]))) return SPMVB200_ERR_INVALID;
 
     SpmvProblem<OffT, ValT> p;
     p.n_rows = (int32_t)n_rows;
@@ -54,7 +55,7 @@ int run(int kind, int64_t n_rows, int64_t n_cols, int64_t nnz, const void *Ap, c
     p.y = static_cast<ValT *>(y);
     p.alpha_dev = static_cast<const ValT *>(alpha_dev);
     p.peers.n = n_peers;
-    for (int i = 0; i < kMaxPeers; ++i) p.peers.ptr[i] = i < n_peers ? y_peers[i] : nullptr;
+    for (int i = 0; i < kMaxPeers; ++i) p.peers.ptr[i] = i < (n_peers < 0 ? 1 : n_peers) ? y_peers[i] : nullptr;
     p.stream = stream;
 
     switch (kind) {

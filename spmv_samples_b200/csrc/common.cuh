@@ -177,15 +177,37 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint3
         : "memory");
 }
 
-// gather of x with an L2 policy (evict_last keeps x resident against the Aj/Ax stream)
+// gather of x with an L2 policy (evict_last keeps x resident against the Aj/Ax stream).
+// SPMV_GATHER_MODE selects the load flavour at compile time (ablation; default 0):
+//   0  ld.global.nc + L2::cache_hint(evict_last)      1  ld.global.cg (bypass L1)
+//   2  ld.global.nc.L1::no_allocate + L2 hint         3  plain ld.global.nc
+#ifndef SPMV_GATHER_MODE
+#define SPMV_GATHER_MODE 0
+#endif
 __device__ __forceinline__ float ldg_hint(const float *p, uint64_t policy) {
     float v;
+#if SPMV_GATHER_MODE == 0
     asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(policy));
+#elif SPMV_GATHER_MODE == 1
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+#elif SPMV_GATHER_MODE == 2
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(policy));
+#else
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+#endif
     return v;
 }
 __device__ __forceinline__ double ldg_hint(const double *p, uint64_t policy) {
     double v;
+#if SPMV_GATHER_MODE == 0
     asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy));
+#elif SPMV_GATHER_MODE == 1
+    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
+#elif SPMV_GATHER_MODE == 2
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy));
+#else
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+#endif
     return v;
 }
 
@@ -230,13 +252,46 @@ __device__ __forceinline__ ValT subwarp_sum(ValT v) {
     return v;
 }
 
+// NVLink multicast store (NVLS): one store, the switch replicates it into every GPU bound to
+// the multicast object, the storing GPU included.
+__device__ __forceinline__ void multimem_st(float *mc, float v) {
+    asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(mc), "f"(v) : "memory");
+}
+__device__ __forceinline__ void multimem_st(double *mc, double v) {
+    asm volatile("multimem.st.weak.global.f64 [%0], %1;" ::"l"(mc), "d"(v) : "memory");
+}
+
+// fan a y value out to the replicas of the other GPUs: peers.n > 0 -> that many peer-mapped
+// pointers; peers.n == -1 -> ptr[0] is a multicast address covering all replicas
+template <typename ValT>
+__device__ __forceinline__ void store_peers(const PeerOut &peers, int64_t row, ValT v) {
+    if (peers.n < 0) {
+        multimem_st(static_cast<ValT *>(peers.ptr[0]) + row, v);
+    } else {
+#pragma unroll
+        for (int i = 0; i < kMaxPeers; ++i)
+            if (i < peers.n) static_cast<ValT *>(peers.ptr[i])[row] = v;
+    }
+}
+
 // y store fanned out to the peer replicas
 template <typename ValT>
 __device__ __forceinline__ void store_y(ValT *y, const PeerOut &peers, int64_t row, ValT v) {
     y[row] = v;
-#pragma unroll
-    for (int i = 0; i < kMaxPeers; ++i)
-        if (i < peers.n) static_cast<ValT *>(peers.ptr[i])[row] = v;
+    store_peers(peers, row, v);
+}
+// Row stores of the SpMV kernels: the local y always; the peer replicas only when the row has
+// nonzeros.  An empty row's y is 0 on every step, and the replicas start out zeroed
+// (dist.PowerIteration), so its value never has to cross NVLink.  On R-MAT scale 27, 61 % of
+// the rows are empty and the rank owning the sparse tail would otherwise send 7 x 218 MB per
+// step -- the fused exchange was egress-bound on that one rank (4.2 ms/step at 8 GPUs against
+// a 2.1 ms kernel).  A row whose nonzeros all lie in earlier tiles gets its value from the
+// merge fixup, which always stores to the peers.
+template <typename ValT>
+__device__ __forceinline__ void store_y_nonempty(ValT *y, const PeerOut &peers, int64_t row, ValT v,
+                                                 bool has_nonzeros) {
+    y[row] = v;
+    if (has_nonzeros) store_peers(peers, row, v);
 }
 #endif  // __CUDACC__
 

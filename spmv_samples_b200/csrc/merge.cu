@@ -266,7 +266,7 @@ merge_tile_tma_kernel(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
         const int q = (int)((int64_t)rend[j] - sy);
         const int b = j > 0 ? (int)((int64_t)rend[j - 1] - sy) : 0;
         const ValT sum = q > b ? scan[q - 1] : (ValT)0;
-        store_y(y, peers, (int64_t)sx + j, alpha * sum);
+        store_y_nonempty(y, peers, (int64_t)sx + j, alpha * sum, q > b);
     }
     if (tid == 0) {
         // nonzeros after the last row end of the tile belong to row ex: carry them out
@@ -437,7 +437,7 @@ merge_tile_reg_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
         const int q = (int)((int64_t)__ldg(Ap + sx + 1 + j) - sy);
         const int b = b64 > 0 ? (int)b64 : 0;
         const ValT sum = q > b ? scan[q - 1] : (ValT)0;
-        store_y(y, peers, (int64_t)sx + j, alpha * sum);
+        store_y_nonempty(y, peers, (int64_t)sx + j, alpha * sum, q > b);
     }
     if (tid == 0) {
         const int64_t lq = R > 0 ? (int64_t)__ldg(Ap + ex) - sy : 0;

@@ -202,7 +202,7 @@ template <typename OffT, typename ValT>
 int launch_cusparse(const SpmvProblem<OffT, ValT> &p) {
     if (p.n_rows <= 0 || p.n_cols <= 0) return SPMVB200_OK;
     // the baseline is plain y = A*x: no device alpha, no peer fan-out
-    if (p.peers.n > 0 || p.alpha_dev) return SPMVB200_ERR_UNSUPPORTED;
+    if (p.peers.n != 0 || p.alpha_dev) return SPMVB200_ERR_UNSUPPORTED;
     std::lock_guard<std::mutex> lk(g_cs_mu);
     int dev = -1;
     SPMV_CUDA_TRY(cudaGetDevice(&dev));

@@ -40,7 +40,7 @@ vector_kernel(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
     if (active && !is_long)
         sum = row_partial<T, OffT, ValT>(s, e, nnz, lane, Aj, Ax, x, pol_stream, pol_x);
     sum = subwarp_sum<T>(sum);
-    if (active && !is_long && lane == 0) store_y(y, peers, row, alpha * sum);
+    if (active && !is_long && lane == 0) store_y_nonempty(y, peers, row, alpha * sum, e > s);
     warp_long_rows<T, OffT, ValT>(is_long, s, e, row, nnz, Aj, Ax, x, y, peers, alpha, pol_stream,
                                   pol_x);
 }

@@ -5,8 +5,13 @@ BASELINE.json: rows are split by nnz-balanced merge-path boundaries (the same de
 that cuts tiles), every rank keeps its rows of A and a full replica of x, and after each
 SpMV every rank needs everybody's slice of the new x.
 
-Two exchanges:
+Three exchanges ("auto" tries them in this order):
 
+  "mc"    x replicas live in torch symmetric memory bound to one NVLink multicast object
+          (NVLS): the SpMV kernel stores each y value once with multimem.st and the NVSwitch
+          replicates it into every GPU's replica, so a rank's egress is its own slice, not
+          (P-1) copies of it -- which matters because nnz-balanced row blocks have very unequal
+          row counts (on R-MAT scale 27 one of 8 ranks owns 40 % of the rows).
   "p2p"   the SpMV kernel itself stores each y value into the local replica AND into the
           peer-mapped replicas of the other GPUs (cudaIpc handles over NVLink / NVSwitch), so
           the all-gather is fused into the kernel's epilogue and overlaps its own gathers; the
@@ -100,7 +105,7 @@ def shard_rows(global_csr: generate.Csr, rank: int, world: int, value_seed=None)
 class PowerIteration:
     """x <- A x / ||A x||, A row-sharded over `world` ranks (world = 1: the whole matrix)."""
 
-    def __init__(self, shard: Shard, n_rows_global: int, kind: str = "auto", exchange: str = "p2p",
+    def __init__(self, shard: Shard, n_rows_global: int, kind: str = "auto", exchange: str = "auto",
                  group=None, host_ops=None):
         """host_ops: TEST HOOK ONLY -- an object with spmv(csr, x, y, alpha) for CPU tensors, so
         the exchange protocol (double buffering, uneven all-gather, norm all-reduce) can be
@@ -118,32 +123,67 @@ class PowerIteration:
         self.dtype = m.Ax.dtype
         self.vbits = m.Ax.element_size() * 8
         assert m.n_cols == n_rows_global, "power iteration needs a square matrix"
+        self.exchange = exchange if shard.world > 1 else "none"
+        self.exchange_note = ""
+        self._raw, self._symm = [], []
+        self.peer_ptrs = [[], []]   # per buffer: peers' base addresses mapped into this process
+        self.mc_ptrs = [0, 0]       # per buffer: NVLink multicast address (exchange "mc")
         if host_ops is None:
             if not torch.cuda.is_available():
                 raise RuntimeError("PowerIteration needs a CUDA device; there is no CPU path")
-            self._raw = [_RawDeviceArray(self.n, self.dtype) for _ in range(2)]
-            self.xbuf = [r.tensor() for r in self._raw]
             dev = "cuda"
+            if self.exchange == "auto" and shard.world <= 4:
+                # measured on R-MAT scale 27: peer stores win at 2 and 4 GPUs (8.15 / 4.30 ms per
+                # step vs 8.43 / 4.42 with multicast), multicast wins at 8 (2.32 vs 2.94 ms)
+                self.exchange = "p2p"
+            if self.exchange in ("mc", "auto"):
+                try:
+                    self._alloc_symmetric()
+                    self.exchange = "mc"
+                except Exception as e:  # no symmetric memory / no NVLS here
+                    self.exchange_note = f"multicast unavailable ({type(e).__name__}: {e}); "
+                    self.exchange = "p2p"
+                    self._symm, self.xbuf = [], []
+            if self.exchange != "mc":
+                self._raw = [_RawDeviceArray(self.n, self.dtype) for _ in range(2)]
+                self.xbuf = [r.tensor() for r in self._raw]
+            if self.exchange == "p2p":
+                try:
+                    self._map_peers()
+                except Exception as e:  # no IPC / no peer access: fall back to NCCL, and say so
+                    self.exchange = "nccl"
+                    self.exchange_note += f"p2p unavailable ({type(e).__name__}: {e}); nccl all-gather"
         else:
-            self._raw = []
             self.xbuf = [torch.zeros(self.n, dtype=self.dtype) for _ in range(2)]
             dev = "cpu"
-            if exchange == "p2p":
-                exchange = "nccl"  # collectives only on the host
+            if self.exchange != "none":
+                self.exchange = "nccl"  # collectives only on the host
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
         self.alpha = torch.ones(1, dtype=self.dtype, device=dev)
         self.step_no = 0
-        self.exchange = exchange if self.world > 1 else "none"
-        self.peer_ptrs = [[], []]  # per buffer: peers' base addresses (mapped into this process)
-        if self.exchange == "p2p":
-            try:
-                self._map_peers()
-            except Exception as e:  # no IPC / no peer access: fall back to NCCL, and say so
-                self.exchange = "nccl"
-                self.exchange_note = f"p2p unavailable ({e}); nccl all-gather"
         self.reset()
 
     # ------------------------------------------------------------------ setup
+    def _alloc_symmetric(self):
+        """x replicas in torch symmetric memory: every rank allocates the same buffers, the
+        rendezvous maps them into one NVLink multicast object (NVLS), and a single
+        multimem.st from the SpMV kernel lands in all replicas."""
+        import torch.distributed._symmetric_memory as symm_mem
+        group = self.group if self.group is not None else self.dist.group.WORLD
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.xbuf = [symm_mem.empty(self.n, dtype=self.dtype, device=dev) for _ in range(2)]
+        for t in self.xbuf:
+            try:
+                h = symm_mem.rendezvous(t, group.group_name)
+            except TypeError:
+                h = symm_mem.rendezvous(t, group=group)
+            self._symm.append(h)
+        self.mc_ptrs = [int(getattr(h, "multicast_ptr", 0) or 0) for h in self._symm]
+        ok = torch.tensor([int(all(self.mc_ptrs))], device="cuda")
+        self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0:
+            raise RuntimeError("no multicast pointer")
+
     def _map_peers(self):
         handles = [r.ipc_handle() for r in self._raw]
         gathered = [None] * self.world
@@ -174,10 +214,21 @@ class PowerIteration:
         x = self.xbuf[cur]
         y = self.xbuf[nxt][s.row_begin:s.row_end]
         item = self.xbuf[nxt].element_size()
-        peers = [p + s.row_begin * item for p in self.peer_ptrs[nxt]] if self.exchange == "p2p" else []
+        if self.exchange == "mc":
+            peers = [self.mc_ptrs[nxt] + s.row_begin * item]
+        elif self.exchange == "p2p":
+            peers = [p + s.row_begin * item for p in self.peer_ptrs[nxt]]
+        else:
+            peers = []
         if self.host_ops is None:
             spmv_mod.spmv_ex(self.kind, m.Ap, m.Aj, m.Ax, x, y, n_cols=self.n, alpha_dev=self.alpha,
-                             y_peers=peers)
+                             y_peers=peers, multicast=self.exchange == "mc")
+            if self.step_no == 0 and self.exchange in ("p2p", "mc"):
+                # The kernels send only rows that have nonzeros to the peers; an empty row's
+                # entry must therefore already be 0 in every replica.  Buffer 1 starts zeroed;
+                # buffer 0 held x0 and is cleared here, after this step's kernel has read it
+                # and before the step barrier lets any peer store into it.
+                self.xbuf[0].zero_()
             L = _lib.lib()
             st = L.spmvb200_sum_squares(self.vbits, y.numel(), y.data_ptr(), self.sumsq.data_ptr(),
                                         torch.cuda.current_stream().cuda_stream)
@@ -223,6 +274,7 @@ class PowerIteration:
                 _lib.lib().spmvb200_ipc_close(C.c_void_p(p))
         self.peer_ptrs = [[], []]
         self.xbuf = []
+        self._symm = []
         for r in self._raw:
             r.free()
 

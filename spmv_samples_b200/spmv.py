@@ -110,9 +110,11 @@ def SpMV(kind_str, n_rows, n_cols, nnz, Ap, Aj, Ax, x, y, stream=None):
     fn(n_rows, n_cols, nnz, Ap, Aj, Ax, x, y, stream)
 
 
-def spmv_ex(kind_str, Ap, Aj, Ax, x, y, n_cols=None, alpha_dev=None, y_peers=(), stream=None):
+def spmv_ex(kind_str, Ap, Aj, Ax, x, y, n_cols=None, alpha_dev=None, y_peers=(), stream=None,
+            multicast=False):
     """Untyped entry (spmvb200_spmv): optional device alpha, optional peer replicas of y.
-    y_peers: iterable of raw device addresses (ints), each indexed like y."""
+    y_peers: iterable of raw device addresses (ints), each indexed like y; with
+    multicast=True it holds ONE NVLink multicast address that reaches every replica."""
     _check_tensors(Ap, Aj, Ax, x, y)
     if kind_str not in KIND_IDS:
         raise SpMVKindError(f'SpMV kind "{kind_str}" is NOT SUPPROT')
@@ -127,7 +129,9 @@ def spmv_ex(kind_str, Ap, Aj, Ax, x, y, n_cols=None, alpha_dev=None, y_peers=(),
                                   y.data_ptr())
     a.alpha_dev = alpha_dev.data_ptr() if alpha_dev is not None else None
     peers = list(y_peers)
-    a.n_peers = len(peers)
+    if multicast and len(peers) != 1:
+        raise ValueError("multicast=True takes exactly one address")
+    a.n_peers = -1 if multicast else len(peers)
     arr = (C.c_void_p * max(1, len(peers)))(*peers)
     a.y_peers = C.cast(arr, C.POINTER(C.c_void_p))
     a.stream = (stream if stream is not None else torch.cuda.current_stream()).cuda_stream

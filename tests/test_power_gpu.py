@@ -133,7 +133,7 @@ def _rank_main(rank, world, port, exchange, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+@pytest.mark.parametrize("exchange", ["mc", "p2p", "nccl"])
 def test_two_gpu_sharded_iteration_matches_single_gpu(tmp_path, exchange):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")

@@ -305,7 +305,8 @@ def test_device_alpha_and_peer_replicas(kind):
     x = g.gen_x(4, 1500)
     dAp, dAj, dAx, dx = dev(Ap), dev(Aj), dev(Ax), dev(x)
     y = torch.empty(6000, device="cuda")
-    rep = [torch.full((6000 + 10,), float("nan"), device="cuda") for _ in range(3)]
+    # replicas start zeroed: rows without nonzeros are not sent to the peers (their y is 0)
+    rep = [torch.zeros(6000 + 10, device="cuda") for _ in range(3)]
     alpha = torch.tensor([0.375], device="cuda")
     # replicas receive the rows at an offset, the way a peer's x_next + row_begin does
     peers = [r.data_ptr() + 4 * i * 3 for i, r in enumerate(rep)]
