@@ -36,6 +36,7 @@ std::map<std::string, int64_t> &options() {
     static std::map<std::string, int64_t> o = {
         {"l2_window", 0},        // 1: attach an L2 access-policy persistence window over x
         {"vector_width", 0},     // 0: from row statistics; else force lanes per row (1..32)
+        {"vector_rows_per_subwarp", 0},  // 0/1: one row per sub-warp; 4: interleaved ablation kernel
         {"light_width", 0},      // same for the dynamic-row kernel
         {"light_rows_per_claim", 0},  // 0: automatic
         {"time_main_kernel", 0}, // 1: cudaEvent bracket around each call's dominant kernel

@@ -28,7 +28,7 @@ def run(*args):
 
 
 @pytest.mark.parametrize("cfg", ["synthetic:c1:96", "synthetic:c2:8192", "synthetic:c3:12",
-                                 "synthetic:c4:256", "synthetic:c5:13"])
+                                 "synthetic:c4:4096", "synthetic:c5:13"])
 def test_driver_all_kinds_pass_on_synthetic(cfg):
     kinds = ["merge", "vector", "light", "auto"] + ([] if "c5" in cfg else ["cusparse"])
     r = run(cfg, *kinds, "--iters", "5", "--x", "random")

@@ -382,3 +382,27 @@ def test_merge_tma_staged_variant_edge_cases(case):
     finally:
         spmv.set_option("merge_staging", 0)
     assert_within_tolerance(y, Ap, Aj, Ax, x, f"{case}/merge-tma")
+
+
+@pytest.mark.parametrize("rps", [1, 4])
+@pytest.mark.parametrize("width", [1, 2, 4, 8])
+@pytest.mark.parametrize("case", ["ragged", "lap2d", "o64_f64"])
+def test_vector_rows_per_subwarp_variants(case, width, rps):
+    """The interleaved multi-row kernel (4 rows per sub-warp) and the one-row kernel agree with
+    the oracle for every width, including rows much longer than the width (whole-warp path)."""
+    from spmv_samples_b200 import spmv
+    if case == "ragged":
+        Ap, Aj, Ax = g.ragged(7001, 3000, 5.0, 11, heavy_rows=4, heavy_len=4000)
+    elif case == "lap2d":
+        Ap, Aj, Ax = g.lap2d(97)
+    else:
+        Ap, Aj, Ax = g.ragged(3001, 900, 7.0, 12, dtype=np.float64, offset_dtype=np.int64, heavy_len=900)
+    x = g.gen_x(5, int(Aj.max()) + 1, Ax.dtype)
+    spmv.set_option("vector_width", width)
+    spmv.set_option("vector_rows_per_subwarp", rps)
+    try:
+        y = run_kind("vector", Ap, Aj, Ax, x)
+    finally:
+        spmv.set_option("vector_width", 0)
+        spmv.set_option("vector_rows_per_subwarp", 0)
+    assert_within_tolerance(y, Ap, Aj, Ax, x, f"vector {case} width {width} rps {rps}")

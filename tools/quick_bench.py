@@ -34,6 +34,22 @@ for cfg in a.configs.split(","):
     st = spmv.row_stats(m.Ap, nnz=m.nnz)
     print(f"== {cfg} rows={m.n_rows} nnz={m.nnz} bytes={m.algorithmic_bytes()} mean={st['mean_row_len']:.2f} "
           f"max={st['max_row_len']} std={st['std_row_len']:.1f} auto->{st['chosen_kind']}/w{st['chosen_width']}", flush=True)
+    # yardstick: a plain device copy moving the same number of bytes (half read, half written)
+    try:
+        half = m.algorithmic_bytes() // 8
+        src = torch.empty(half, dtype=torch.float32, device="cuda"); dst = torch.empty_like(src)
+        ts = []
+        for _ in range(a.iters):
+            if not a.no_flush:
+                flush.zero_()
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            e0.record(); dst.copy_(src); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        ts.sort(); t = ts[len(ts) // 2]
+        print(f"   {'(copy)':9s} {t*1e6:10.1f} us  {half*8/t/1e9:8.1f} GB/s   torch copy of the same byte count", flush=True)
+        del src, dst
+    except Exception as e:
+        print("   (copy) failed:", e)
     for kind in a.kinds.split(","):
         try:
             for _ in range(3):
