@@ -15,11 +15,13 @@
 #include "spmv/cusparse_baseline.hpp"
 #include "spmv/dynamic_rows.hpp"
 #include "spmv/host_check.hpp"
+#include "spmv/merge_generalized.hpp"
 #include "spmv/merge_path.hpp"
 
 /// SPMV kind strings and its function
 #define SPMV_KINDS                                                             \
     X("merge", SpMV_merge_path)                                                \
+    X("merge_genl", SpMV_merge_generalized)                                    \
     X("vector", SpMV_csr_vector)                                               \
     X("light", SpMV_dynamic_rows)                                              \
     X("auto", SpMV_auto_select)                                                \

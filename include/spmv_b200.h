@@ -106,6 +106,19 @@ SPMVB200_DECLARE_KIND(cusparse)
  * peer buffers must hold 0 at the positions of empty rows -- zero them once.
  * n_peers == -1: y_peers[0] is an NVLink multicast address (NVLS; e.g. the multicast_ptr of a
  * torch symmetric-memory buffer) and every such row is stored once with multimem.st. */
+/* Generalised SpMV  y[r] = REDUCE_k COMBINE(Ax[k], x[Aj[k]])  from IDENTITY: the fixed menu that
+ * stands in for the template functor of the reference's SpMV_merge_based_generalized
+ * (merge_genl/merge_genl.cuh:19-38, cpu_navie.hpp:20-35).  Served by the merge-path kernel only
+ * (kind merge or auto), as in the reference.  Empty rows yield IDENTITY. */
+enum {
+    SPMVB200_SEMIRING_PLUS_TIMES = 0, /* 0,    a*x,            u+v        (ordinary SpMV)     */
+    SPMVB200_SEMIRING_MIN_PLUS = 1,   /* +inf, a+x,            min(u,v)   (shortest paths)    */
+    SPMVB200_SEMIRING_MAX_PLUS = 2,   /* -inf, a+x,            max(u,v)   (longest paths)     */
+    SPMVB200_SEMIRING_OR_AND = 3      /* 0,    a!=0 && x!=0,   max(u,v)   (reachability, 0/1) */
+};
+/* beta_dev: optional DEVICE pointer to one value-typed scalar: y = alpha*A*x + beta*y (plus-times
+ * only; merge-path kernel; merge_based/agent_spmv_orig.cuh:425-433 HAS_BETA).  NULL means 0 and y
+ * is not read.  Fields after `stream` default to plus-times / no beta when zero-initialised. */
 typedef struct {
     int32_t kind;
     int32_t offset_bits;
@@ -122,6 +135,9 @@ typedef struct {
     const void *alpha_dev;
     void *const *y_peers;
     spmvb200_stream_t stream;
+    int32_t semiring;
+    int32_t reserved;
+    const void *beta_dev;
 } spmvb200_args_t;
 SPMVB200_API int spmvb200_spmv(const spmvb200_args_t *args);
 

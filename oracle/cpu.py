@@ -112,6 +112,37 @@ def abs_scale(Ap, Aj, Ax, x) -> np.ndarray:
     return s
 
 
+SEMIRINGS = {"min_plus": 1, "max_plus": 2, "or_and": 3}
+
+
+def spmv_semiring(Ap, Aj, Ax, x, semiring: str) -> np.ndarray:
+    """Generalised SpMV over a fixed semiring (cpu_navie.hpp:20-35, SpMV_genl_cpu_navie)."""
+    _check(Ap, Aj, Ax)
+    n_rows = Ap.shape[0] - 1
+    x = np.ascontiguousarray(x, dtype=Ax.dtype)
+    y = np.empty(n_rows, dtype=Ax.dtype)
+    fn = getattr(lib(), f"oracle_genl_{_off_tag(Ap)}_{_val_tag(Ax)}")
+    fn.restype = C.c_int
+    rc = fn(C.c_int(SEMIRINGS[semiring]), C.c_int64(n_rows), _p(Ap), _p(Aj), _p(Ax), _p(x), _p(y))
+    assert rc == 0
+    return y
+
+
+def ref_spmv_semiring(Ap, Aj, Ax, x, semiring: str) -> np.ndarray:
+    """The reference's SpMV_genl_cpu_navie with the same functor (int32 offsets)."""
+    _check(Ap, Aj, Ax)
+    assert Ap.dtype == np.int32
+    n_rows = Ap.shape[0] - 1
+    x = np.ascontiguousarray(x, dtype=Ax.dtype)
+    y = np.empty(n_rows, dtype=Ax.dtype)
+    fn = getattr(ref(), f"ref_genl_o32_{_val_tag(Ax)}")
+    fn.restype = C.c_int
+    rc = fn(C.c_int(SEMIRINGS[semiring]), C.c_int32(n_rows), C.c_int32(x.shape[0]),
+            C.c_int32(int(Ap[-1])), _p(Ap), _p(Aj), _p(Ax), _p(x), _p(y))
+    assert rc == 0
+    return y
+
+
 def spmv_mt(Ap, Aj, Ax, x, n_threads: int):
     """Row-block-parallel run of the same loop; returns (y, threads_used)."""
     _check(Ap, Aj, Ax)

@@ -66,7 +66,46 @@ struct AbsFunctor {
     static double reduce(double a, double b) { return a + b; }
 };
 
+// the fixed semiring menu of include/spmv_b200.h as functor_t's for SpMV_genl_cpu_navie
+template <typename T> struct MinPlusFunctor {
+    static T initialize() { return std::numeric_limits<T>::infinity(); }
+    static T combine(T a, T x) { return a + x; }
+    static T reduce(T u, T v) { return u < v ? u : v; }
+};
+template <typename T> struct MaxPlusFunctor {
+    static T initialize() { return -std::numeric_limits<T>::infinity(); }
+    static T combine(T a, T x) { return a + x; }
+    static T reduce(T u, T v) { return u > v ? u : v; }
+};
+template <typename T> struct OrAndFunctor {
+    static T initialize() { return T(0); }
+    static T combine(T a, T x) { return (a != T(0) && x != T(0)) ? T(1) : T(0); }
+    static T reduce(T u, T v) { return u > v ? u : v; }
+};
+
 }  // namespace
+
+// ---- SpMV_genl_cpu_navie with the semiring menu (1 min-plus, 2 max-plus, 3 or-and) ----
+REF_API int ref_genl_o32_f32(int semiring, int32_t n_rows, int32_t n_cols, int32_t nnz,
+                             const int32_t *Ap, const int32_t *Aj, const float *Ax, const float *x,
+                             float *y) {
+    switch (semiring) {
+        case 1: SpMV_genl_cpu_navie<MinPlusFunctor<float>, int, int, float, float, float>(n_rows, n_cols, nnz, Ap, Aj, Ax, x, y); return 0;
+        case 2: SpMV_genl_cpu_navie<MaxPlusFunctor<float>, int, int, float, float, float>(n_rows, n_cols, nnz, Ap, Aj, Ax, x, y); return 0;
+        case 3: SpMV_genl_cpu_navie<OrAndFunctor<float>, int, int, float, float, float>(n_rows, n_cols, nnz, Ap, Aj, Ax, x, y); return 0;
+        default: return 1;
+    }
+}
+REF_API int ref_genl_o32_f64(int semiring, int32_t n_rows, int32_t n_cols, int32_t nnz,
+                             const int32_t *Ap, const int32_t *Aj, const double *Ax, const double *x,
+                             double *y) {
+    switch (semiring) {
+        case 1: SpMV_genl_cpu_navie<MinPlusFunctor<double>, int, int, double, double, double>(n_rows, n_cols, nnz, Ap, Aj, Ax, x, y); return 0;
+        case 2: SpMV_genl_cpu_navie<MaxPlusFunctor<double>, int, int, double, double, double>(n_rows, n_cols, nnz, Ap, Aj, Ax, x, y); return 0;
+        case 3: SpMV_genl_cpu_navie<OrAndFunctor<double>, int, int, double, double, double>(n_rows, n_cols, nnz, Ap, Aj, Ax, x, y); return 0;
+        default: return 1;
+    }
+}
 
 // ---- SpMV_cpu_navie, the instantiations the configs need (32-bit offsets only:
 // the reference's inner counter is index_t, cpu_navie.hpp:12) ----

@@ -83,6 +83,35 @@ DEF_ABS(oracle_abs_o32_f64, int32_t, double)
 DEF_ABS(oracle_abs_o64_f64, int64_t, double)
 
 /* ------------------------------------------------------------------------- *
+ * Generalised (semiring) SpMV: y[r] = REDUCE_k COMBINE(Ax[k], x[Aj[k]]) from IDENTITY,
+ * sequential, k ascending.  Reference: include/spmv/cpu_navie.hpp:20-35
+ * (SpMV_genl_cpu_navie<functor_t>) with the functors of the fixed menu that
+ * include/spmv_b200.h offers in place of a template functor:
+ *   1 min-plus (+inf, a+x, min)   2 max-plus (-inf, a+x, max)   3 or-and (0, a!=0&&x!=0, max)
+ * ------------------------------------------------------------------------- */
+#define DEF_GENL(NAME, OFF_T, VAL_T)                                                   \
+    ORACLE_API int NAME(int semiring, int64_t n_rows, const OFF_T *Ap, const int32_t *Aj, \
+                        const VAL_T *Ax, const VAL_T *x, VAL_T *y) {                   \
+        if (semiring < 1 || semiring > 3) return 1;                                    \
+        for (int64_t row = 0; row < n_rows; ++row) {                                   \
+            VAL_T sum = semiring == 1 ? (VAL_T)INFINITY                                \
+                        : semiring == 2 ? (VAL_T)-INFINITY : (VAL_T)0;                 \
+            for (OFF_T k = Ap[row]; k < Ap[row + 1]; ++k) {                            \
+                const VAL_T a = Ax[k], xv = x[Aj[k]];                                  \
+                if (semiring == 1) { const VAL_T c = a + xv; sum = sum < c ? sum : c; } \
+                else if (semiring == 2) { const VAL_T c = a + xv; sum = sum > c ? sum : c; } \
+                else { const VAL_T c = (a != 0 && xv != 0) ? (VAL_T)1 : (VAL_T)0; sum = sum > c ? sum : c; } \
+            }                                                                          \
+            y[row] = sum;                                                              \
+        }                                                                              \
+        return 0;                                                                      \
+    }
+DEF_GENL(oracle_genl_o32_f32, int32_t, float)
+DEF_GENL(oracle_genl_o64_f32, int64_t, float)
+DEF_GENL(oracle_genl_o32_f64, int32_t, double)
+DEF_GENL(oracle_genl_o64_f64, int64_t, double)
+
+/* ------------------------------------------------------------------------- *
  * Row-parallel driver of the same loop for the CPU baseline timing: threads take
  * contiguous row blocks, each block runs the sequential loop above unchanged.
  * Not reference code (the reference is single threaded); reported with its

@@ -99,6 +99,8 @@ struct SpmvProblem {
 
 // launchers (one translation unit each)
 template <typename OffT, typename ValT> int launch_merge(const SpmvProblem<OffT, ValT> &p);
+template <typename OffT, typename ValT>
+int launch_merge_genl(const SpmvProblem<OffT, ValT> &p, int semiring, const ValT *beta_dev);
 template <typename OffT, typename ValT> int launch_vector(const SpmvProblem<OffT, ValT> &p, int width);
 template <typename OffT, typename ValT> int launch_light(const SpmvProblem<OffT, ValT> &p, int width);
 template <typename OffT, typename ValT> int launch_cusparse(const SpmvProblem<OffT, ValT> &p);

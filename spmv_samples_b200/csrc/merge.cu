@@ -487,6 +487,250 @@ merge_fixup_kernel(int32_t n_rows, int64_t num_tiles, const int32_t *__restrict_
     store_y(y, peers, (int64_t)row, y[row] + alpha * sum);
 }
 
+// ----------------------------------------------------- generalised (semiring) tile kernel
+// y[r] = REDUCE_k COMBINE(Ax[k], x[Aj[k]]) starting from IDENTITY, the capability of the
+// reference's SpMV_merge_based_generalized (merge_genl/merge_genl.cuh:19-38 with its
+// functor_t{initialize, combine, reduce}; CPU twin cpu_navie.hpp:20-35).  A template functor
+// cannot cross a C ABI, so the menu is fixed (SPMVB200_SEMIRING_*).  Same tile algorithm as
+// merge_tile_reg_body; kept separate so the plus-times hot path is not perturbed.  With
+// plus-times this kernel also serves y = alpha*A*x + beta*y.
+template <typename ValT> struct SrPlusTimes {
+    static constexpr bool kLinear = true;
+    static __device__ __forceinline__ ValT identity() { return (ValT)0; }
+    static __device__ __forceinline__ ValT combine(ValT a, ValT x) { return a * x; }
+    static __device__ __forceinline__ ValT reduce(ValT u, ValT v) { return u + v; }
+};
+template <typename ValT> struct SrMinPlus {
+    static constexpr bool kLinear = false;
+    static __device__ __forceinline__ ValT identity() { return (ValT)INFINITY; }
+    static __device__ __forceinline__ ValT combine(ValT a, ValT x) { return a + x; }
+    static __device__ __forceinline__ ValT reduce(ValT u, ValT v) { return u < v ? u : v; }
+};
+template <typename ValT> struct SrMaxPlus {
+    static constexpr bool kLinear = false;
+    static __device__ __forceinline__ ValT identity() { return (ValT)-INFINITY; }
+    static __device__ __forceinline__ ValT combine(ValT a, ValT x) { return a + x; }
+    static __device__ __forceinline__ ValT reduce(ValT u, ValT v) { return u > v ? u : v; }
+};
+template <typename ValT> struct SrOrAnd {
+    static constexpr bool kLinear = false;
+    static __device__ __forceinline__ ValT identity() { return (ValT)0; }
+    static __device__ __forceinline__ ValT combine(ValT a, ValT x) {
+        return (a != (ValT)0 && x != (ValT)0) ? (ValT)1 : (ValT)0;
+    }
+    static __device__ __forceinline__ ValT reduce(ValT u, ValT v) { return u > v ? u : v; }
+};
+
+template <typename S, typename OffT, typename ValT>
+__global__ void __launch_bounds__(kMergeBlock)
+merge_tile_genl_kernel(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
+                       const int32_t *__restrict__ Aj, const ValT *__restrict__ Ax,
+                       const ValT *__restrict__ x, ValT *__restrict__ y,
+                       const ValT *__restrict__ alpha_dev, const ValT *__restrict__ beta_dev,
+                       PeerOut peers, const int32_t *__restrict__ coords_x,
+                       int32_t *__restrict__ carry_row, ValT *__restrict__ carry_val) {
+    constexpr int IPT = kMergeIPT;
+    __shared__ __align__(16) ValT s_scan[kSlots];
+    __shared__ __align__(16) unsigned char s_flag[kSlots];
+    __shared__ ValT s_wval[kMergeBlock / 32];
+    __shared__ int s_wflag[kMergeBlock / 32];
+
+    const int tid = threadIdx.x;
+    const int64_t tile = blockIdx.x;
+    const int64_t total = (int64_t)n_rows + (int64_t)nnz;
+    const int64_t d0 = tile * kMergeTile;
+    const int64_t d1 = d0 + kMergeTile < total ? d0 + kMergeTile : total;
+    const int32_t sx = __ldg(coords_x + tile);
+    const int32_t ex = __ldg(coords_x + tile + 1);
+    const int64_t sy = d0 - sx;
+    const int R = ex - sx;
+    const int Z = (int)((d1 - ex) - sy);
+    const int shift = (int)(sy & 3);
+    const int64_t a0 = sy - shift;
+    const ValT ident = S::identity();
+
+    *reinterpret_cast<uint2 *>(s_flag + tid * IPT) = make_uint2(0u, 0u);
+    const int slot0 = tid * IPT;
+    const uint64_t pol_stream = policy_evict_first();
+    const uint64_t pol_x = policy_evict_last();
+    int c[IPT];
+    ValT p[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        c[k] = 0;
+        p[k] = (ValT)0;
+    }
+    if (slot0 < shift + Z) {
+        const int64_t g = a0 + slot0;
+        if (g + IPT <= (int64_t)nnz) {
+            const int4 ca = ldg_stream_int4(Aj + g, pol_stream);
+            const int4 cb = ldg_stream_int4(Aj + g + 4, pol_stream);
+            c[0] = ca.x; c[1] = ca.y; c[2] = ca.z; c[3] = ca.w;
+            c[4] = cb.x; c[5] = cb.y; c[6] = cb.z; c[7] = cb.w;
+            LoadVals<ValT>::vec8(Ax + g, pol_stream, p);
+        } else {
+#pragma unroll
+            for (int k = 0; k < IPT; ++k) {
+                if (g + k < (int64_t)nnz) {
+                    c[k] = __ldg(Aj + g + k);
+                    p[k] = __ldg(Ax + g + k);
+                }
+            }
+        }
+    }
+    const ValT alpha = (S::kLinear && alpha_dev) ? __ldg(alpha_dev) : (ValT)1;
+    const ValT beta = (S::kLinear && beta_dev) ? __ldg(beta_dev) : (ValT)0;
+    __syncthreads();
+    for (int j = tid; j < R; j += kMergeBlock) {
+        const int64_t q = (int64_t)__ldg(Ap + sx + 1 + j) - sy;
+        if (q < Z) s_flag[(int)q + shift] = 1;
+    }
+    {
+        ValT xv[IPT];
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+            const int i = slot0 + k - shift;
+            xv[k] = (i >= 0 && i < Z) ? ldg_hint(x + c[k], pol_x) : (ValT)0;
+        }
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+            const int i = slot0 + k - shift;
+            p[k] = (i >= 0 && i < Z) ? S::combine(p[k], xv[k]) : ident;
+        }
+    }
+    __syncthreads();
+
+    const uint2 fw = *reinterpret_cast<const uint2 *>(s_flag + slot0);
+    const unsigned long long fbits = ((unsigned long long)fw.y << 32) | fw.x;
+    int flag = fbits != 0ull;
+    ValT val = ident;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) val = ((fbits >> (8 * k)) & 1ull) ? p[k] : S::reduce(val, p[k]);
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const ValT pvv = __shfl_up_sync(0xffffffffu, val, d);
+        const int pf = __shfl_up_sync(0xffffffffu, flag, d);
+        if (lane >= d) {
+            if (!flag) val = S::reduce(pvv, val);
+            flag |= pf;
+        }
+    }
+    if (lane == 31) {
+        s_wval[warp] = val;
+        s_wflag[warp] = flag;
+    }
+    ValT ev = __shfl_up_sync(0xffffffffu, val, 1);
+    int ef = __shfl_up_sync(0xffffffffu, flag, 1);
+    if (lane == 0) {
+        ev = ident;
+        ef = 0;
+    }
+    __syncthreads();
+    ValT wv = ident;
+#pragma unroll
+    for (int w = 0; w < kMergeBlock / 32; ++w) {
+        if (w < warp) {
+            const ValT v = s_wval[w];
+            wv = s_wflag[w] ? v : S::reduce(wv, v);
+        }
+    }
+    ValT run = ef ? ev : S::reduce(wv, ev);
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        run = ((fbits >> (8 * k)) & 1ull) ? p[k] : S::reduce(run, p[k]);
+        p[k] = run;
+    }
+    sts8(s_scan + slot0, p);
+    __syncthreads();
+
+    const ValT *scan = s_scan + shift;
+    for (int j = tid; j < R; j += kMergeBlock) {
+        const int64_t b64 = (int64_t)__ldg(Ap + sx + j) - sy;
+        const int q = (int)((int64_t)__ldg(Ap + sx + 1 + j) - sy);
+        const int b = b64 > 0 ? (int)b64 : 0;
+        const ValT sum = q > b ? scan[q - 1] : ident;
+        ValT out = S::kLinear ? alpha * sum : sum;
+        if (S::kLinear && beta_dev) out += beta * y[(int64_t)sx + j];
+        // beta makes every row's value depend on the old y, and a non-zero identity makes empty
+        // rows non-zero: in both cases every row goes to the peers
+        store_y_nonempty(y, peers, (int64_t)sx + j, out, q > b || beta_dev != nullptr || !S::kLinear);
+    }
+    if (tid == 0) {
+        const int64_t lq = R > 0 ? (int64_t)__ldg(Ap + ex) - sy : 0;
+        const int lastq = lq > 0 ? (int)lq : 0;
+        carry_row[tile] = ex;
+        carry_val[tile] = Z > lastq ? scan[Z - 1] : ident;
+    }
+}
+
+template <typename S, typename ValT>
+__global__ void __launch_bounds__(256)
+merge_fixup_genl_kernel(int32_t n_rows, int64_t num_tiles, const int32_t *__restrict__ carry_row,
+                        const ValT *__restrict__ carry_val, ValT *__restrict__ y,
+                        const ValT *__restrict__ alpha_dev, PeerOut peers) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_tiles) return;
+    const int32_t row = carry_row[t];
+    if (row >= n_rows) return;
+    if (t > 0 && carry_row[t - 1] == row) return;
+    ValT sum = carry_val[t];
+    for (int64_t u = t + 1; u < num_tiles && carry_row[u] == row; ++u) sum = S::reduce(sum, carry_val[u]);
+    if (S::kLinear) {
+        const ValT alpha = alpha_dev ? __ldg(alpha_dev) : (ValT)1;
+        store_y(y, peers, (int64_t)row, y[row] + alpha * sum);
+    } else {
+        store_y(y, peers, (int64_t)row, S::reduce(y[row], sum));
+    }
+}
+
+}  // namespace
+
+template <typename S, typename OffT, typename ValT>
+static int launch_merge_genl_s(const SpmvProblem<OffT, ValT> &p, const ValT *beta_dev) {
+    const int64_t total = (int64_t)p.n_rows + (int64_t)p.nnz;
+    const int64_t num_tiles = (total + kMergeTile - 1) / kMergeTile;
+    if (num_tiles <= 0) return SPMVB200_OK;
+    if (num_tiles > 0x7fffffffLL) return SPMVB200_ERR_UNSUPPORTED;
+    void *coords = nullptr, *crow = nullptr, *cval = nullptr;
+    SPMV_TRY(scratch_get(p.stream, SCRATCH_COORDS, (size_t)(num_tiles + 1) * sizeof(int32_t), &coords));
+    SPMV_TRY(scratch_get(p.stream, SCRATCH_CARRY_ROW, (size_t)num_tiles * sizeof(int32_t), &crow));
+    SPMV_TRY(scratch_get(p.stream, SCRATCH_CARRY_VAL, (size_t)num_tiles * sizeof(ValT), &cval));
+    SPMV_TRY(launch_partition<OffT>(p.n_rows, p.nnz, p.Ap, kMergeTile, num_tiles + 1,
+                                    static_cast<int32_t *>(coords), p.stream));
+    {
+        KernelTimerScope timed(p.stream);
+        merge_tile_genl_kernel<S, OffT, ValT><<<(unsigned)num_tiles, kMergeBlock, 0, p.stream>>>(
+            p.n_rows, p.nnz, p.Ap, p.Aj, p.Ax, p.x, p.y, p.alpha_dev, beta_dev, p.peers,
+            (const int32_t *)coords, static_cast<int32_t *>(crow), static_cast<ValT *>(cval));
+    }
+    SPMV_LAUNCH_CHECK();
+    if (num_tiles > 1) {
+        const int64_t blocks = (num_tiles + 255) / 256;
+        merge_fixup_genl_kernel<S, ValT><<<(unsigned)blocks, 256, 0, p.stream>>>(
+            p.n_rows, num_tiles, (const int32_t *)crow, (const ValT *)cval, p.y, p.alpha_dev, p.peers);
+        SPMV_LAUNCH_CHECK();
+    }
+    return SPMVB200_OK;
+}
+
+template <typename OffT, typename ValT>
+int launch_merge_genl(const SpmvProblem<OffT, ValT> &p, int semiring, const ValT *beta_dev) {
+    if (semiring != SPMVB200_SEMIRING_PLUS_TIMES && (p.alpha_dev || beta_dev)) return SPMVB200_ERR_UNSUPPORTED;
+    switch (semiring) {
+        case SPMVB200_SEMIRING_PLUS_TIMES: return launch_merge_genl_s<SrPlusTimes<ValT>>(p, beta_dev);
+        case SPMVB200_SEMIRING_MIN_PLUS: return launch_merge_genl_s<SrMinPlus<ValT>>(p, beta_dev);
+        case SPMVB200_SEMIRING_MAX_PLUS: return launch_merge_genl_s<SrMaxPlus<ValT>>(p, beta_dev);
+        case SPMVB200_SEMIRING_OR_AND: return launch_merge_genl_s<SrOrAnd<ValT>>(p, beta_dev);
+        default: return SPMVB200_ERR_INVALID;
+    }
+}
+template int launch_merge_genl<int32_t, float>(const SpmvProblem<int32_t, float> &, int, const float *);
+template int launch_merge_genl<int32_t, double>(const SpmvProblem<int32_t, double> &, int, const double *);
+template int launch_merge_genl<int64_t, float>(const SpmvProblem<int64_t, float> &, int, const float *);
+template int launch_merge_genl<int64_t, double>(const SpmvProblem<int64_t, double> &, int, const double *);
+
+namespace {
 }  // namespace
 
 template <typename OffT>

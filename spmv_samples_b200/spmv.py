@@ -111,10 +111,13 @@ def SpMV(kind_str, n_rows, n_cols, nnz, Ap, Aj, Ax, x, y, stream=None):
 
 
 def spmv_ex(kind_str, Ap, Aj, Ax, x, y, n_cols=None, alpha_dev=None, y_peers=(), stream=None,
-            multicast=False):
+            multicast=False, semiring="plus_times", beta_dev=None):
     """Untyped entry (spmvb200_spmv): optional device alpha, optional peer replicas of y.
     y_peers: iterable of raw device addresses (ints), each indexed like y; with
-    multicast=True it holds ONE NVLink multicast address that reaches every replica."""
+    multicast=True it holds ONE NVLink multicast address that reaches every replica.
+    semiring: "plus_times" | "min_plus" | "max_plus" | "or_and" (merge-path kernel; the fixed
+    menu standing in for the reference's functor_t, merge_genl/merge_genl.cuh:19-38);
+    beta_dev: device scalar, y = alpha*A*x + beta*y (plus-times only)."""
     _check_tensors(Ap, Aj, Ax, x, y)
     if kind_str not in KIND_IDS:
         raise SpMVKindError(f'SpMV kind "{kind_str}" is NOT SUPPROT')
@@ -128,6 +131,8 @@ def spmv_ex(kind_str, Ap, Aj, Ax, x, y, n_cols=None, alpha_dev=None, y_peers=(),
     a.Ap, a.Aj, a.Ax, a.x, a.y = (Ap.data_ptr(), Aj.data_ptr(), Ax.data_ptr(), x.data_ptr(),
                                   y.data_ptr())
     a.alpha_dev = alpha_dev.data_ptr() if alpha_dev is not None else None
+    a.beta_dev = beta_dev.data_ptr() if beta_dev is not None else None
+    a.semiring = _lib.SEMIRINGS[semiring]
     peers = list(y_peers)
     if multicast and len(peers) != 1:
         raise ValueError("multicast=True takes exactly one address")

@@ -57,6 +57,8 @@ def main():
         out["y_ref"] = cpu.ref_spmv(Ap, Aj, Ax, x)
         out["y_ref64"] = cpu.ref_spmv_fp64(Ap, Aj, Ax, x)
         out["abs_ref"] = cpu.ref_abs_scale(Ap, Aj, Ax, x)
+        for sr in cpu.SEMIRINGS:   # SpMV_genl_cpu_navie with the fixed functor menu
+            out[f"y_{sr}"] = cpu.ref_spmv_semiring(Ap, Aj, Ax, x, sr)
         for tile in TILES:
             tiles = (n_rows + nnz + tile - 1) // tile
             diags = np.minimum(np.arange(tiles + 1, dtype=np.int64) * tile, n_rows + nnz)

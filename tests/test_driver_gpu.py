@@ -30,7 +30,7 @@ def run(*args):
 @pytest.mark.parametrize("cfg", ["synthetic:c1:96", "synthetic:c2:8192", "synthetic:c3:12",
                                  "synthetic:c4:4096", "synthetic:c5:13"])
 def test_driver_all_kinds_pass_on_synthetic(cfg):
-    kinds = ["merge", "vector", "light", "auto"] + ([] if "c5" in cfg else ["cusparse"])
+    kinds = ["merge", "merge_genl", "vector", "light", "auto"] + ([] if "c5" in cfg else ["cusparse"])
     r = run(cfg, *kinds, "--iters", "5", "--x", "random")
     assert r.returncode == 0, r.stdout + r.stderr
     assert "Compute delta:" in r.stdout and "Time cost" in r.stdout

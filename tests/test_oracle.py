@@ -28,6 +28,9 @@ def test_oracle_matches_reference_golden(name):
     assert np.array_equal(cpu.spmv(Ap, Aj, Ax, x), d["y_ref"])            # bit-exact
     assert np.array_equal(cpu.spmv_fp64(Ap, Aj, Ax, x), d["y_ref64"])
     assert np.array_equal(cpu.abs_scale(Ap, Aj, Ax, x), d["abs_ref"])
+    for sr in cpu.SEMIRINGS:
+        assert np.array_equal(cpu.spmv_semiring(Ap, Aj, Ax, x, sr), d[f"y_{sr}"])
+        assert np.array_equal(cpu.spmv_semiring(Ap.astype(np.int64), Aj, Ax, x, sr), d[f"y_{sr}"])
     for tile in (2048, 896, 320):
         cx, cy = cpu.merge_tile_coords(Ap, tile)
         assert np.array_equal(np.stack([cx, cy], 1), d[f"coords_{tile}"])
@@ -111,6 +114,9 @@ class TestAgainstReferenceLive:
         assert np.array_equal(cpu.abs_scale(Ap, Aj, Ax, x), cpu.ref_abs_scale(Ap, Aj, Ax, x))
         y, used = cpu.ref_spmv_mt(Ap, Aj, Ax, x, 4)
         assert np.array_equal(y, cpu.ref_spmv(Ap, Aj, Ax, x))
+        for sr in cpu.SEMIRINGS:
+            assert np.array_equal(cpu.spmv_semiring(Ap, Aj, Ax, x, sr),
+                                  cpu.ref_spmv_semiring(Ap, Aj, Ax, x, sr))
 
     def test_spmv_f64_and_o64(self):
         Ap, Aj, Ax = g.ragged(1000, 300, 20.0, 5, dtype=np.float64)

@@ -406,3 +406,65 @@ def test_vector_rows_per_subwarp_variants(case, width, rps):
         spmv.set_option("vector_width", 0)
         spmv.set_option("vector_rows_per_subwarp", 0)
     assert_within_tolerance(y, Ap, Aj, Ax, x, f"vector {case} width {width} rps {rps}")
+
+
+# ------------------------------------------------------------------ semirings and beta
+@pytest.mark.parametrize("semiring", ["min_plus", "max_plus", "or_and"])
+@pytest.mark.parametrize("name", golden_cases())
+def test_semiring_golden_bit_exact(name, semiring):
+    """min/max/or reductions do not round, so the CUDA result must equal the reference's
+    SpMV_genl_cpu_navie output (committed golden vector) bit for bit, in any summation order."""
+    from spmv_samples_b200 import spmv
+    d = load_golden(name)
+    dAp, dAj, dAx, dx = dev(d["Ap"]), dev(d["Aj"]), dev(d["Ax"]), dev(d["x"])
+    y = torch.full((d["Ap"].shape[0] - 1,), float("nan"), dtype=dAx.dtype, device="cuda")
+    spmv.spmv_ex("merge", dAp, dAj, dAx, dx, y, semiring=semiring)
+    torch.cuda.synchronize()
+    assert np.array_equal(y.cpu().numpy(), d[f"y_{semiring}"]), (name, semiring)
+
+
+@pytest.mark.parametrize("semiring", ["min_plus", "max_plus", "or_and"])
+@pytest.mark.parametrize("family", ["rmat_s16", "ragged_heavy", "ragged_mostly_empty", "ragged_f64",
+                                    "rmat_s14_o64"])
+def test_semiring_family_bit_exact(family, semiring):
+    from spmv_samples_b200 import spmv
+    Ap, Aj, Ax = FAMILIES[family]()
+    x = g.gen_x(17, int(Aj.max()) + 1, Ax.dtype)
+    x[::5] = 0                                           # so that or-and sees zeros
+    dAp, dAj, dAx, dx = dev(Ap), dev(Aj), dev(Ax), dev(x)
+    y = torch.full((Ap.shape[0] - 1,), float("nan"), dtype=dAx.dtype, device="cuda")
+    spmv.spmv_ex("auto", dAp, dAj, dAx, dx, y, semiring=semiring)
+    torch.cuda.synchronize()
+    assert np.array_equal(y.cpu().numpy(), cpu.spmv_semiring(Ap, Aj, Ax, x, semiring))
+
+
+@pytest.mark.parametrize("family", ["rmat_s16", "ragged_heavy", "longrow_f64_512x2048"])
+def test_alpha_beta(family):
+    """y = alpha*A*x + beta*y_old through the generalised merge kernel."""
+    from spmv_samples_b200 import spmv
+    Ap, Aj, Ax = FAMILIES[family]()
+    n = Ap.shape[0] - 1
+    x = g.gen_x(17, int(Aj.max()) + 1, Ax.dtype)
+    y0 = g.gen_x(19, n, Ax.dtype)
+    dAp, dAj, dAx, dx = dev(Ap), dev(Aj), dev(Ax), dev(x)
+    y = dev(y0.copy())
+    alpha = torch.tensor([1.5], dtype=dAx.dtype, device="cuda")
+    beta = torch.tensor([-0.25], dtype=dAx.dtype, device="cuda")
+    spmv.spmv_ex("merge", dAp, dAj, dAx, dx, y, alpha_dev=alpha, beta_dev=beta)
+    torch.cuda.synchronize()
+    expect = 1.5 * cpu.spmv_fp64(Ap, Aj, Ax, x) - 0.25 * y0.astype(np.float64)
+    scale = 1.5 * cpu.abs_scale(Ap, Aj, Ax, x) + 0.25 * np.abs(y0.astype(np.float64))
+    tol = TOL[np.dtype(Ax.dtype)]
+    assert np.all(np.abs(y.cpu().numpy().astype(np.float64) - expect) <= tol * scale)
+
+
+def test_semiring_needs_the_merge_kernel():
+    from spmv_samples_b200 import spmv, _lib
+    Ap, Aj, Ax = g.uniform_rows(64, 64, 16, 1)
+    d = [dev(a) for a in (Ap, Aj, Ax, g.gen_x(1, 64))]
+    y = torch.zeros(64, device="cuda")
+    with pytest.raises(_lib.SpmvB200Error) as ei:
+        spmv.spmv_ex("vector", *d, y, semiring="min_plus")
+    assert ei.value.status == 4
+    with pytest.raises(_lib.SpmvB200Error):
+        spmv.spmv_ex("merge", *d, y, semiring="min_plus", alpha_dev=torch.ones(1, device="cuda"))
