@@ -367,28 +367,43 @@ def own_arm(args, rank, world, local_rank):
     e2e = None
     if args.e2e_steps > 0:
         mat = CsrMatrix.from_device(local)
-        xh = torch.empty(n_cols, dtype=local.Ax.dtype, pin_memory=True)
-        yh = torch.empty(local.n_rows, dtype=local.Ax.dtype, pin_memory=True)
-        xh.copy_(it.current_x().cpu())
-        xn, yn = xh.numpy(), yh.numpy()
+        xs = [torch.empty(n_cols, dtype=local.Ax.dtype, pin_memory=True) for _ in range(2)]
+        ys = [torch.empty(local.n_rows, dtype=local.Ax.dtype, pin_memory=True) for _ in range(2)]
+        xs[0].copy_(it.current_x().cpu())
+        xs[1].copy_(xs[0])
+        xn, yn = [t.numpy() for t in xs], [t.numpy() for t in ys]
+
+        def timed(fn):
+            barrier()
+            t0 = time.perf_counter()
+            fn()
+            dt = time.perf_counter() - t0
+            td = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(td, op=dist.ReduceOp.MAX)
+            return float(td.item())
+
+        k = args.e2e_steps
         for _ in range(2):
-            mat.spmv(xn, yn, kind=args.kind)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            mat.spmv(xn, yn, kind=args.kind)
-        dt = time.perf_counter() - t0
-        td = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(td, op=dist.ReduceOp.MAX)
-        dt = float(td.item())
-        e2e = {"value": 2.0 * nnz_total * args.e2e_steps / dt / 1e9, "unit": UNIT,
-               "h2d_bytes_per_step": int(n_cols * xh.element_size()),
-               "d2h_bytes_per_step": int(local.n_rows * yh.element_size()),
-               "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
-               "api": "spmv_samples_b200.matrix.CsrMatrix.spmv (spmvb200_matrix_spmv_host): "
-                      "matrix resident (uploaded once, as reference main.cu:55-69), per-rank "
-                      "x H2D + SpMV + y D2H per step"}
+            mat.spmv(xn[0], yn[0], kind=args.kind)
+        # one call at a time: upload, kernel, download, back to back
+        dt_serial = timed(lambda: [mat.spmv(xn[0], yn[0], kind=args.kind) for _ in range(k)])
+        # the pipelined call for a sequence of right-hand sides: two slots in flight, so one
+        # step's upload overlaps the previous step's kernel and download
+        mat.spmv_many([xn[i & 1] for i in range(2)], [yn[i & 1] for i in range(2)], kind=args.kind)
+        dt = timed(lambda: mat.spmv_many([xn[i & 1] for i in range(k)], [yn[i & 1] for i in range(k)],
+                                         kind=args.kind))
+        e2e = {"value": 2.0 * nnz_total * k / dt / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": int(n_cols * xs[0].element_size()),
+               "d2h_bytes_per_step": int(local.n_rows * ys[0].element_size()),
+               "steps": k, "ms_per_step": dt / k * 1e3,
+               "serial_value": 2.0 * nnz_total * k / dt_serial / 1e9,
+               "serial_ms_per_step": dt_serial / k * 1e3,
+               "api": "spmv_samples_b200.matrix.CsrMatrix.spmv_many (spmvb200_matrix_submit_host / "
+                      "_wait): matrix resident (uploaded once, as reference main.cu:55-69); every "
+                      "step uploads its x from pinned host memory, runs the SpMV and downloads y; two "
+                      "steps in flight on two streams.  serial_value: CsrMatrix.spmv, one step at a "
+                      "time"}
         mat.close()
 
     it.close()

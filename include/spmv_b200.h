@@ -202,6 +202,14 @@ SPMVB200_API int spmvb200_matrix_create_from_device(int offset_bits, int value_b
                                                     spmvb200_matrix_t **out);
 SPMVB200_API int spmvb200_matrix_spmv_host(spmvb200_matrix_t *m, int kind, const void *x_host,
                                            void *y_host);
+/* Pipelined form for a sequence of independent right-hand sides: two slots (0, 1), each with its
+ * own stream and device x/y.  submit enqueues H2D(x) -> SpMV -> D2H(y) on the slot's stream and
+ * returns; wait blocks until that slot's y_host is complete.  Alternating the slots overlaps one
+ * call's upload with the other's kernel and download (both copy engines + the SMs busy).
+ * x_host / y_host should be pinned, and must stay untouched until the slot has been waited on. */
+SPMVB200_API int spmvb200_matrix_submit_host(spmvb200_matrix_t *m, int kind, int slot,
+                                             const void *x_host, void *y_host);
+SPMVB200_API int spmvb200_matrix_wait(spmvb200_matrix_t *m, int slot);
 SPMVB200_API void spmvb200_matrix_destroy(spmvb200_matrix_t *m);
 
 /* ---- device-side data layer: synthetic generators and COO -> CSR ------------------------

@@ -111,6 +111,8 @@ def lib() -> C.CDLL:
     L.spmvb200_device_malloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
     L.spmvb200_device_free.argtypes = [C.c_void_p]
     L.spmvb200_matrix_spmv_host.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.spmvb200_matrix_submit_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.spmvb200_matrix_wait.argtypes = [C.c_void_p, C.c_int]
     L.spmvb200_matrix_destroy.argtypes = [C.c_void_p]
     L.spmvb200_matrix_destroy.restype = None
     L.spmvb200_ipc_export.argtypes = [C.c_void_p, C.c_char_p]

@@ -208,6 +208,9 @@ struct spmvb200_matrix {
     int32_t *Aj = nullptr;
     cudaStream_t stream = nullptr;
     bool owns_csr = true;
+    // second pipeline slot (own stream and x/y buffers), created on first use
+    void *x1 = nullptr, *y1 = nullptr;
+    cudaStream_t stream1 = nullptr;
 };
 
 namespace spmvb200 {
@@ -318,11 +321,20 @@ int spmvb200_matrix_create(int offset_bits, int value_bits, int64_t n_rows, int6
     return SPMVB200_OK;
 }
 
-int spmvb200_matrix_spmv_host(spmvb200_matrix_t *m, int kind, const void *x_host, void *y_host) {
-    if (!m || (!x_host && m->n_cols > 0) || (!y_host && m->n_rows > 0)) return SPMVB200_ERR_INVALID;
+int spmvb200_matrix_submit_host(spmvb200_matrix_t *m, int kind, int slot, const void *x_host,
+                                void *y_host) {
+    if (!m || slot < 0 || slot > 1 || (!x_host && m->n_cols > 0) || (!y_host && m->n_rows > 0))
+        return SPMVB200_ERR_INVALID;
     const size_t vb = m->value_bits / 8;
+    if (slot == 1 && !m->stream1) {
+        SPMV_CUDA_TRY(cudaStreamCreateWithFlags(&m->stream1, cudaStreamNonBlocking));
+        SPMV_CUDA_TRY(cudaMalloc(&m->x1, (size_t)(m->n_cols ? m->n_cols : 1) * vb));
+        SPMV_CUDA_TRY(cudaMalloc(&m->y1, (size_t)(m->n_rows ? m->n_rows : 1) * vb));
+    }
+    cudaStream_t st = slot ? m->stream1 : m->stream;
+    void *dx = slot ? m->x1 : m->x, *dy = slot ? m->y1 : m->y;
     if (m->n_cols > 0)
-        SPMV_CUDA_TRY(cudaMemcpyAsync(m->x, x_host, (size_t)m->n_cols * vb, cudaMemcpyHostToDevice, m->stream));
+        SPMV_CUDA_TRY(cudaMemcpyAsync(dx, x_host, (size_t)m->n_cols * vb, cudaMemcpyHostToDevice, st));
     spmvb200_args_t a;
     std::memset(&a, 0, sizeof(a));
     a.kind = kind;
@@ -334,16 +346,27 @@ int spmvb200_matrix_spmv_host(spmvb200_matrix_t *m, int kind, const void *x_host
     a.Ap = m->Ap;
     a.Aj = m->Aj;
     a.Ax = m->Ax;
-    a.x = m->x;
-    a.y = m->y;
-    a.stream = m->stream;
+    a.x = dx;
+    a.y = dy;
+    a.stream = st;
     SPMV_TRY(spmvb200_spmv(&a));
     if (m->n_rows > 0) {
-        if (m->n_cols == 0) SPMV_CUDA_TRY(cudaMemsetAsync(m->y, 0, (size_t)m->n_rows * vb, m->stream));
-        SPMV_CUDA_TRY(cudaMemcpyAsync(y_host, m->y, (size_t)m->n_rows * vb, cudaMemcpyDeviceToHost, m->stream));
+        if (m->n_cols == 0) SPMV_CUDA_TRY(cudaMemsetAsync(dy, 0, (size_t)m->n_rows * vb, st));
+        SPMV_CUDA_TRY(cudaMemcpyAsync(y_host, dy, (size_t)m->n_rows * vb, cudaMemcpyDeviceToHost, st));
     }
-    SPMV_CUDA_TRY(cudaStreamSynchronize(m->stream));
     return SPMVB200_OK;
+}
+
+int spmvb200_matrix_wait(spmvb200_matrix_t *m, int slot) {
+    if (!m || slot < 0 || slot > 1) return SPMVB200_ERR_INVALID;
+    cudaStream_t st = slot ? m->stream1 : m->stream;
+    if (st) SPMV_CUDA_TRY(cudaStreamSynchronize(st));
+    return SPMVB200_OK;
+}
+
+int spmvb200_matrix_spmv_host(spmvb200_matrix_t *m, int kind, const void *x_host, void *y_host) {
+    SPMV_TRY(spmvb200_matrix_submit_host(m, kind, 0, x_host, y_host));
+    return spmvb200_matrix_wait(m, 0);
 }
 
 void spmvb200_matrix_destroy(spmvb200_matrix_t *m) {
@@ -354,9 +377,13 @@ void spmvb200_matrix_destroy(spmvb200_matrix_t *m) {
         if (m->Aj) cudaFree(m->Aj);
         if (m->Ax) cudaFree(m->Ax);
     }
+    if (m->stream1) cudaStreamSynchronize(m->stream1);
     if (m->x) cudaFree(m->x);
     if (m->y) cudaFree(m->y);
+    if (m->x1) cudaFree(m->x1);
+    if (m->y1) cudaFree(m->y1);
     if (m->stream) cudaStreamDestroy(m->stream);
+    if (m->stream1) cudaStreamDestroy(m->stream1);
     delete m;
 }
 

@@ -66,6 +66,31 @@ class CsrMatrix:
         _lib.check(st, "spmvb200_matrix_spmv_host")
         return y
 
+    def submit(self, slot: int, x: np.ndarray, y: np.ndarray, kind: str = "auto") -> None:
+        """Asynchronous y = A @ x on pipeline slot 0 or 1 (own stream, own device buffers): the
+        upload, the kernel and the download are enqueued and the call returns.  x and y should be
+        pinned host arrays and must not be touched until wait(slot)."""
+        if kind not in KIND_IDS:
+            raise SpMVKindError(f'SpMV kind "{kind}" is NOT SUPPROT')
+        if x.dtype != self.dtype or x.shape[0] != self.n_cols or y.dtype != self.dtype \
+                or y.shape[0] != self.n_rows or not x.flags.c_contiguous or not y.flags.c_contiguous:
+            raise ValueError("x / y must be contiguous vectors of the matrix dtype and shape")
+        st = _lib.lib().spmvb200_matrix_submit_host(self._h, KIND_IDS[kind], int(slot), x.ctypes.data,
+                                                    y.ctypes.data)
+        _lib.check(st, "spmvb200_matrix_submit_host")
+
+    def wait(self, slot: int) -> None:
+        _lib.check(_lib.lib().spmvb200_matrix_wait(self._h, int(slot)), "spmvb200_matrix_wait")
+
+    def spmv_many(self, xs, ys, kind: str = "auto") -> None:
+        """ys[i] = A @ xs[i] for a sequence of independent right-hand sides, two in flight."""
+        for i, (x, y) in enumerate(zip(xs, ys)):
+            if i >= 2:
+                self.wait(i & 1)
+            self.submit(i & 1, x, y, kind)
+        self.wait(0)
+        self.wait(1)
+
     def close(self):
         if getattr(self, "_h", None):
             _lib.lib().spmvb200_matrix_destroy(self._h)
