@@ -141,6 +141,32 @@ typedef struct {
 } spmvb200_args_t;
 SPMVB200_API int spmvb200_spmv(const spmvb200_args_t *args);
 
+/* ---- K right-hand sides at once (SpMM), K in {2, 4, 8} -----------------------------------
+ * Y = alpha * A * X with X [n_cols x k] and Y [n_rows x k] row-major with leading dimensions
+ * ldx, ldy (in elements).  New with respect to the reference; the only
+ * way past the gather bound of CSR SpMV: one gather returns k values.  X and Y must be 16-byte
+ * aligned (8 for k = 2 floats) and ldx, ldy must keep every row so aligned, else
+ * SPMVB200_ERR_ALIGNMENT.  alpha_dev as in spmvb200_spmv. */
+typedef struct {
+    int32_t offset_bits;
+    int32_t value_bits;
+    int32_t k;
+    int32_t reserved;
+    int64_t n_rows;
+    int64_t n_cols;
+    int64_t nnz;
+    const void *Ap;
+    const int32_t *Aj;
+    const void *Ax;
+    const void *X;
+    int64_t ldx;
+    void *Y;
+    int64_t ldy;
+    const void *alpha_dev;
+    spmvb200_stream_t stream;
+} spmvb200_spmm_args_t;
+SPMVB200_API int spmvb200_spmm(const spmvb200_spmm_args_t *args);
+
 /* ---- merge-path partition, exposed so parity tests can demand bit-exact coordinates --- */
 /* Row coordinate of the merge path on each diagonal min(t * tile_items, n_rows + nnz),
  * t = 0 .. n_coords-1, written to the DEVICE array coords_x (int32).  The nonzero

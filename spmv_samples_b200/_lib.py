@@ -39,6 +39,16 @@ class Args(C.Structure):
     ]
 
 
+class SpmmArgs(C.Structure):
+    _fields_ = [
+        ("offset_bits", C.c_int32), ("value_bits", C.c_int32), ("k", C.c_int32), ("reserved", C.c_int32),
+        ("n_rows", C.c_int64), ("n_cols", C.c_int64), ("nnz", C.c_int64),
+        ("Ap", C.c_void_p), ("Aj", C.c_void_p), ("Ax", C.c_void_p), ("X", C.c_void_p),
+        ("ldx", C.c_int64), ("Y", C.c_void_p), ("ldy", C.c_int64), ("alpha_dev", C.c_void_p),
+        ("stream", C.c_void_p),
+    ]
+
+
 class RowStats(C.Structure):
     _fields_ = [
         ("n_rows", C.c_int64), ("nnz", C.c_int64), ("max_row_len", C.c_int64),
@@ -73,6 +83,8 @@ def lib() -> C.CDLL:
     L.spmvb200_version.restype = C.c_char_p
     L.spmvb200_spmv.argtypes = [C.POINTER(Args)]
     L.spmvb200_spmv.restype = C.c_int
+    L.spmvb200_spmm.argtypes = [C.POINTER(SpmmArgs)]
+    L.spmvb200_spmm.restype = C.c_int
     L.spmvb200_launch_count.restype = C.c_int64
     L.spmvb200_get_option.restype = C.c_int64
     L.spmvb200_get_option.argtypes = [C.c_char_p]

@@ -117,6 +117,35 @@ SPMVB200_DEFINE_KIND(cusparse, SPMVB200_KIND_CUSPARSE)
 
 int spmvb200_spmv(const spmvb200_args_t *args) { return run_untyped(args); }
 
+int spmvb200_spmm(const spmvb200_spmm_args_t *a) {
+    if (!a || a->n_rows < 0 || a->n_cols < 0 || a->nnz < 0) return SPMVB200_ERR_INVALID;
+    if (a->n_rows > 0x7fffffffLL || a->n_cols > 0x7fffffffLL) return SPMVB200_ERR_INVALID;
+    if (a->k != 2 && a->k != 4 && a->k != 8) return SPMVB200_ERR_UNSUPPORTED;
+    if (a->n_rows == 0 || a->n_cols == 0) return SPMVB200_OK;
+    if (!a->Ap || !a->Y || (a->nnz > 0 && (!a->Aj || !a->Ax || !a->X))) return SPMVB200_ERR_INVALID;
+    if (a->ldx < a->k || a->ldy < a->k) return SPMVB200_ERR_INVALID;
+    if (a->offset_bits == 32 && a->nnz > 0x7fffffffLL - 4096) return SPMVB200_ERR_UNSUPPORTED;
+    if (!aligned16(a->Ap) || !aligned16(a->Aj) || !aligned16(a->Ax)) return SPMVB200_ERR_ALIGNMENT;
+    const size_t vb = a->value_bits / 8;
+    const size_t row_align = (size_t)a->k * vb >= 16 ? 16 : 8;
+    auto ok = [&](const void *p, int64_t ld) {
+        return (reinterpret_cast<uintptr_t>(p) % row_align) == 0 && ((size_t)ld * vb) % row_align == 0;
+    };
+    if (!ok(a->X, a->ldx) || !ok(a->Y, a->ldy)) return SPMVB200_ERR_ALIGNMENT;
+    cudaStream_t s = static_cast<cudaStream_t>(a->stream);
+#define GO(O, V)                                                                                      \
+    return launch_spmm<O, V>(a->k, (int32_t)a->n_rows, (int32_t)a->n_cols, (O)a->nnz,                  \
+                             static_cast<const O *>(a->Ap), a->Aj, static_cast<const V *>(a->Ax),      \
+                             static_cast<const V *>(a->X), a->ldx, static_cast<V *>(a->Y), a->ldy,     \
+                             static_cast<const V *>(a->alpha_dev), s)
+    if (a->offset_bits == 32 && a->value_bits == 32) GO(int32_t, float);
+    if (a->offset_bits == 32 && a->value_bits == 64) GO(int32_t, double);
+    if (a->offset_bits == 64 && a->value_bits == 32) GO(int64_t, float);
+    if (a->offset_bits == 64 && a->value_bits == 64) GO(int64_t, double);
+#undef GO
+    return SPMVB200_ERR_UNSUPPORTED;
+}
+
 // ---- partition / row split -----------------------------------------------------------------
 int spmvb200_merge_path_partition_o32(int32_t n_rows, int32_t nnz, const int32_t *Ap,
                                       int64_t tile_items, int64_t n_coords, int32_t *coords_x,

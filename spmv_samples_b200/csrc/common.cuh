@@ -54,7 +54,7 @@ int current_device_info(const DeviceInfo **out);
 // Per-(device, stream) scratch that survives across calls, grown on demand.
 // Slots keep independent buffers so a kernel can hold several at once.
 enum ScratchSlot { SCRATCH_COORDS = 0, SCRATCH_CARRY_ROW, SCRATCH_CARRY_VAL, SCRATCH_COUNTER,
-                   SCRATCH_STATS, SCRATCH_MISC, SCRATCH_NUM_SLOTS };
+                   SCRATCH_STATS, SCRATCH_MISC, SCRATCH_SPMM_X, SCRATCH_SPMM_Y, SCRATCH_NUM_SLOTS };
 int scratch_get(cudaStream_t stream, ScratchSlot slot, size_t bytes, void **out);
 void scratch_release_all();
 
@@ -112,6 +112,10 @@ template <typename OffT>
 int row_stats(int64_t n_rows, int64_t nnz, const OffT *Ap, spmvb200_row_stats_t *out,
               cudaStream_t stream, bool use_cache);
 int pick_width_from_mean(double mean_row_len);
+template <typename OffT, typename ValT>
+int launch_spmm(int k, int32_t n_rows, int32_t n_cols, OffT nnz, const OffT *Ap, const int32_t *Aj,
+                const ValT *Ax, const ValT *X, int64_t ldx, ValT *Y, int64_t ldy, const ValT *alpha_dev,
+                cudaStream_t stream);
 
 // Launch attribute helper: optional L2 access-policy window over x (option "l2_window").
 struct LaunchCfg {

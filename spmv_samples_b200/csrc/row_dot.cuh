@@ -115,4 +115,52 @@ __device__ __forceinline__ void warp_long_rows(bool is_long, OffT s, OffT e, int
     }
 }
 
+// Third tier: rows longer than kHugeRow are queued in shared memory and reduced by the whole
+// CTA (every thread strides the row with 128-bit loads, block reduction in a fixed order).  A
+// power-law matrix has a few rows of 10^5..10^6 nonzeros; one warp on such a row is a
+// millisecond-long tail (the CSR-vector kernel took 6.2 ms on R-MAT scale 24 before this).
+constexpr int kHugeRow = 16384;
+constexpr int kMaxHugePerCta = 8;
+struct HugeList {
+    int count;
+    long long s[kMaxHugePerCta], e[kMaxHugePerCta], row[kMaxHugePerCta];
+};
+
+// leader lane of a sub-warp queues its row; false when the list is full (the caller then keeps
+// the row on the warp-level path)
+__device__ __forceinline__ bool push_huge(HugeList &hl, long long s, long long e, long long row) {
+    const int slot = atomicAdd(&hl.count, 1);
+    if (slot >= kMaxHugePerCta) return false;
+    hl.s[slot] = s;
+    hl.e[slot] = e;
+    hl.row[slot] = row;
+    return true;
+}
+
+// all threads of the CTA; BLOCK = blockDim.x.  s_red: BLOCK/32 values of shared memory.
+template <int BLOCK, typename OffT, typename ValT>
+__device__ __forceinline__ void cta_huge_rows(HugeList &hl, ValT *s_red, OffT nnz,
+                                              const int32_t *__restrict__ Aj,
+                                              const ValT *__restrict__ Ax,
+                                              const ValT *__restrict__ x, ValT *__restrict__ y,
+                                              const PeerOut &peers, ValT alpha, uint64_t pol_stream,
+                                              uint64_t pol_x) {
+    __syncthreads();  // the list is complete
+    const int n = hl.count < kMaxHugePerCta ? hl.count : kMaxHugePerCta;
+    for (int h = 0; h < n; ++h) {
+        ValT ps = row_partial<BLOCK, OffT, ValT>((OffT)hl.s[h], (OffT)hl.e[h], nnz, (int)threadIdx.x, Aj,
+                                                 Ax, x, pol_stream, pol_x);
+        ps = subwarp_sum<32>(ps);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = ps;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            ValT tot = (ValT)0;
+#pragma unroll
+            for (int w = 0; w < BLOCK / 32; ++w) tot += s_red[w];
+            store_y(y, peers, hl.row[h], alpha * tot);
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace spmvb200

@@ -145,6 +145,30 @@ def spmv_ex(kind_str, Ap, Aj, Ax, x, y, n_cols=None, alpha_dev=None, y_peers=(),
     _lib.check(st, f"spmvb200_spmv[{kind_str}]")
 
 
+def spmm(Ap, Aj, Ax, X, Y, alpha_dev=None, stream=None):
+    """Y = alpha * A @ X for k = X.shape[1] in {2, 4, 8} right-hand sides at once
+    (spmvb200_spmm).  X [n_cols, k] and Y [n_rows, k] are row-major CUDA tensors (a row stride
+    larger than k is allowed)."""
+    if X.dim() != 2 or Y.dim() != 2 or X.shape[1] != Y.shape[1] or X.stride(1) != 1 or Y.stride(1) != 1:
+        raise ValueError("X and Y must be 2-D, row-major, with the same number of columns")
+    if X.dtype != Ax.dtype or Y.dtype != Ax.dtype or not (X.is_cuda and Y.is_cuda):
+        raise TypeError("X, Y must be CUDA tensors of the matrix dtype")
+    a = _lib.SpmmArgs()
+    a.offset_bits = _OFF[Ap.dtype][1]
+    a.value_bits = _VAL[Ax.dtype][1]
+    a.k = X.shape[1]
+    a.n_rows, a.n_cols, a.nnz = Ap.numel() - 1, X.shape[0], Aj.numel()
+    a.Ap, a.Aj, a.Ax = Ap.data_ptr(), Aj.data_ptr(), Ax.data_ptr()
+    a.X, a.ldx, a.Y, a.ldy = X.data_ptr(), X.stride(0), Y.data_ptr(), Y.stride(0)
+    a.alpha_dev = alpha_dev.data_ptr() if alpha_dev is not None else None
+    a.stream = (stream if stream is not None else torch.cuda.current_stream()).cuda_stream
+    if Y.shape[0] != a.n_rows:
+        raise ValueError("Y must have n_rows rows")
+    with torch.cuda.device(Ap.device):
+        st = _lib.lib().spmvb200_spmm(C.byref(a))
+    _lib.check(st, "spmvb200_spmm")
+
+
 def merge_path_partition(Ap, tile_items=None, stream=None):
     """Row coordinates of the merge path on the tile diagonals (int32 CUDA tensor, tiles+1)."""
     L = _lib.lib()
