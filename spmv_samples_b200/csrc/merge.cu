@@ -34,7 +34,10 @@ namespace spmvb200 {
 
 namespace {
 
-constexpr int kMergeBlock = 256;
+#ifndef SPMV_MERGE_BLOCK
+#define SPMV_MERGE_BLOCK 256
+#endif
+constexpr int kMergeBlock = SPMV_MERGE_BLOCK;
 constexpr int kMergeIPT = 8;
 constexpr int kSlots = kMergeBlock * kMergeIPT;  // staged elements per array
 constexpr int kMergeTile = kSlots - 4;           // path items per tile: room for the <=3-element
@@ -302,7 +305,7 @@ template <> struct LoadVals<double> {
     }
 };
 
-template <typename OffT, typename ValT>
+template <bool HAS_PEERS, typename OffT, typename ValT>
 __device__ __forceinline__ void
 merge_tile_reg_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
                     const int32_t *__restrict__ Aj, const ValT *__restrict__ Ax,
@@ -437,7 +440,10 @@ merge_tile_reg_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
         const int q = (int)((int64_t)__ldg(Ap + sx + 1 + j) - sy);
         const int b = b64 > 0 ? (int)b64 : 0;
         const ValT sum = q > b ? scan[q - 1] : (ValT)0;
-        store_y_nonempty(y, peers, (int64_t)sx + j, alpha * sum, q > b);
+        // the peer fan-out is compiled in only when there are peers: its code cost the
+        // (o32, fp32) kernel its 32-register budget (spills; c3 1224 -> 1459 us)
+        if (HAS_PEERS) store_y_nonempty(y, peers, (int64_t)sx + j, alpha * sum, q > b);
+        else y[(int64_t)sx + j] = alpha * sum;
     }
     if (tid == 0) {
         const int64_t lq = R > 0 ? (int64_t)__ldg(Ap + ex) - sy : 0;
@@ -456,15 +462,15 @@ merge_tile_reg_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
     const ValT *__restrict__ Ax, const ValT *__restrict__ x, ValT *__restrict__ y,               \
     const ValT *__restrict__ alpha_dev, PeerOut peers, const int32_t *__restrict__ coords_x,     \
     int32_t *__restrict__ carry_row, ValT *__restrict__ carry_val
-template <typename OffT, typename ValT>
-__global__ void __launch_bounds__(kMergeBlock, 8) merge_tile_reg_kernel_occ8(MERGE_REG_KERNEL_ARGS) {
-    merge_tile_reg_body<OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers, coords_x,
-                                    carry_row, carry_val);
+template <bool HAS_PEERS, typename OffT, typename ValT>
+__global__ void __launch_bounds__(kMergeBlock, 2048 / kMergeBlock) merge_tile_reg_kernel_occ8(MERGE_REG_KERNEL_ARGS) {
+    merge_tile_reg_body<HAS_PEERS, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers, coords_x,
+                                               carry_row, carry_val);
 }
-template <typename OffT, typename ValT>
+template <bool HAS_PEERS, typename OffT, typename ValT>
 __global__ void __launch_bounds__(kMergeBlock) merge_tile_reg_kernel(MERGE_REG_KERNEL_ARGS) {
-    merge_tile_reg_body<OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers, coords_x,
-                                    carry_row, carry_val);
+    merge_tile_reg_body<HAS_PEERS, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers, coords_x,
+                                               carry_row, carry_val);
 }
 #undef MERGE_REG_KERNEL_ARGS
 
@@ -790,7 +796,10 @@ int launch_merge(const SpmvProblem<OffT, ValT> &p) {
                                          static_cast<ValT *>(cval)));
     } else {
         constexpr bool occ8 = sizeof(OffT) == 4 && sizeof(ValT) == 4;
-        auto kernel = occ8 ? merge_tile_reg_kernel_occ8<OffT, ValT> : merge_tile_reg_kernel<OffT, ValT>;
+        const bool has_peers = p.peers.n != 0;
+        auto kernel = has_peers ? merge_tile_reg_kernel<true, OffT, ValT>      // 40 regs, no spill
+                      : occ8    ? merge_tile_reg_kernel_occ8<false, OffT, ValT>
+                                : merge_tile_reg_kernel<false, OffT, ValT>;
         static int64_t attr_carveout = -2;
         if (attr_carveout != carveout) {
             SPMV_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
