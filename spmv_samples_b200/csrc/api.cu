@@ -10,7 +10,7 @@
 #include "common.cuh"
 
 namespace spmvb200 {
-int64_t merge_tile_items();
+int64_t merge_tile_items(int offset_bits);
 void stats_cache_clear();
 void cusparse_plan_clear();
 template <typename ValT>
@@ -163,7 +163,7 @@ int spmvb200_merge_path_partition_o64(int32_t n_rows, int64_t nnz, const int64_t
     return launch_partition<int64_t>(n_rows, nnz, Ap, tile_items, n_coords, coords_x,
                                      static_cast<cudaStream_t>(stream));
 }
-int64_t spmvb200_merge_tile_items(int, int) { return merge_tile_items(); }
+int64_t spmvb200_merge_tile_items(int offset_bits, int) { return merge_tile_items(offset_bits); }
 
 }  // extern "C"
 

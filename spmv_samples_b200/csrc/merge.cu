@@ -305,7 +305,7 @@ template <> struct LoadVals<double> {
     }
 };
 
-template <bool HAS_PEERS, typename OffT, typename ValT>
+template <int BLOCK, bool HAS_PEERS, typename OffT, typename ValT>
 __device__ __forceinline__ void
 merge_tile_reg_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
                     const int32_t *__restrict__ Aj, const ValT *__restrict__ Ax,
@@ -314,16 +314,18 @@ merge_tile_reg_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
                     const int32_t *__restrict__ coords_x, int32_t *__restrict__ carry_row,
                     ValT *__restrict__ carry_val) {
     constexpr int IPT = kMergeIPT;
-    __shared__ __align__(16) ValT s_scan[kSlots];
-    __shared__ __align__(16) unsigned char s_flag[kSlots];
-    __shared__ ValT s_wval[kMergeBlock / 32];
-    __shared__ int s_wflag[kMergeBlock / 32];
+    constexpr int SLOTS = BLOCK * IPT;
+    constexpr int TILE = SLOTS - 4;  // path items per tile
+    __shared__ __align__(16) ValT s_scan[SLOTS];
+    __shared__ __align__(16) unsigned char s_flag[SLOTS];
+    __shared__ ValT s_wval[BLOCK / 32];
+    __shared__ int s_wflag[BLOCK / 32];
 
     const int tid = threadIdx.x;
     const int64_t tile = blockIdx.x;
     const int64_t total = (int64_t)n_rows + (int64_t)nnz;
-    const int64_t d0 = tile * kMergeTile;
-    const int64_t d1 = d0 + kMergeTile < total ? d0 + kMergeTile : total;
+    const int64_t d0 = tile * TILE;
+    const int64_t d1 = d0 + TILE < total ? d0 + TILE : total;
     const int32_t sx = __ldg(coords_x + tile);
     const int32_t ex = __ldg(coords_x + tile + 1);
     const int64_t sy = d0 - sx;
@@ -367,7 +369,7 @@ merge_tile_reg_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
     __syncthreads();  // flags are clear
 
     // ---- row-start flags, one thread per row end (Ap read coalesced, no staging)
-    for (int j = tid; j < R; j += kMergeBlock) {
+    for (int j = tid; j < R; j += BLOCK) {
         const int64_t q = (int64_t)__ldg(Ap + sx + 1 + j) - sy;
         if (q < Z) s_flag[(int)q + shift] = 1;
     }
@@ -417,7 +419,7 @@ merge_tile_reg_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
     __syncthreads();
     ValT wv = (ValT)0;
 #pragma unroll
-    for (int w = 0; w < kMergeBlock / 32; ++w) {
+    for (int w = 0; w < BLOCK / 32; ++w) {
         if (w < warp) {
             const ValT v = s_wval[w];
             wv = s_wflag[w] ? v : wv + v;
@@ -435,7 +437,7 @@ merge_tile_reg_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
     // ---- one thread per row end: the row's total is the scan value at its last nonzero.
     // Row sx+j covers tile-local nonzeros [max(Ap[sx+j]-sy, 0), Ap[sx+j+1]-sy).
     const ValT *scan = s_scan + shift;
-    for (int j = tid; j < R; j += kMergeBlock) {
+    for (int j = tid; j < R; j += BLOCK) {
         const int64_t b64 = (int64_t)__ldg(Ap + sx + j) - sy;
         const int q = (int)((int64_t)__ldg(Ap + sx + 1 + j) - sy);
         const int b = b64 > 0 ? (int)b64 : 0;
@@ -462,14 +464,14 @@ merge_tile_reg_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
     const ValT *__restrict__ Ax, const ValT *__restrict__ x, ValT *__restrict__ y,               \
     const ValT *__restrict__ alpha_dev, PeerOut peers, const int32_t *__restrict__ coords_x,     \
     int32_t *__restrict__ carry_row, ValT *__restrict__ carry_val
-template <bool HAS_PEERS, typename OffT, typename ValT>
-__global__ void __launch_bounds__(kMergeBlock, 2048 / kMergeBlock) merge_tile_reg_kernel_occ8(MERGE_REG_KERNEL_ARGS) {
-    merge_tile_reg_body<HAS_PEERS, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers, coords_x,
+template <int BLOCK, bool HAS_PEERS, typename OffT, typename ValT>
+__global__ void __launch_bounds__(BLOCK, 2048 / BLOCK) merge_tile_reg_kernel_occ8(MERGE_REG_KERNEL_ARGS) {
+    merge_tile_reg_body<BLOCK, HAS_PEERS, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers, coords_x,
                                                carry_row, carry_val);
 }
-template <bool HAS_PEERS, typename OffT, typename ValT>
-__global__ void __launch_bounds__(kMergeBlock) merge_tile_reg_kernel(MERGE_REG_KERNEL_ARGS) {
-    merge_tile_reg_body<HAS_PEERS, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers, coords_x,
+template <int BLOCK, bool HAS_PEERS, typename OffT, typename ValT>
+__global__ void __launch_bounds__(BLOCK) merge_tile_reg_kernel(MERGE_REG_KERNEL_ARGS) {
+    merge_tile_reg_body<BLOCK, HAS_PEERS, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers, coords_x,
                                                carry_row, carry_val);
 }
 #undef MERGE_REG_KERNEL_ARGS
@@ -754,12 +756,23 @@ template int launch_partition<int32_t>(int32_t, int32_t, const int32_t *, int64_
 template int launch_partition<int64_t>(int32_t, int64_t, const int64_t *, int64_t, int64_t,
                                        int32_t *, cudaStream_t);
 
-int64_t merge_tile_items() { return kMergeTile; }
+// CTA size of the register-staged tile kernel: 128 threads (1020-item tiles) with 32-bit offsets,
+// 256 threads (2044-item tiles) with 64-bit offsets -- measured: 128 is 3-8 % faster on c2/c3/c4
+// (shorter barrier waits, 16 CTAs per SM) and 2 % slower on c5.
+template <typename OffT> constexpr int merge_reg_block() { return sizeof(OffT) == 4 ? 128 : 256; }
+
+int64_t merge_tile_items(int offset_bits) {
+    if (option_get("merge_staging", 0) == 1) return kMergeTile;
+    return (offset_bits == 32 ? merge_reg_block<int32_t>() : merge_reg_block<int64_t>()) * kMergeIPT - 4;
+}
 
 template <typename OffT, typename ValT>
 int launch_merge(const SpmvProblem<OffT, ValT> &p) {
+    const bool tma = option_get("merge_staging", 0) == 1;
+    constexpr int RB = merge_reg_block<OffT>();
+    const int tile_items = tma ? kMergeTile : RB * kMergeIPT - 4;
     const int64_t total = (int64_t)p.n_rows + (int64_t)p.nnz;
-    const int64_t num_tiles = (total + kMergeTile - 1) / kMergeTile;
+    const int64_t num_tiles = (total + tile_items - 1) / tile_items;
     if (num_tiles <= 0) return SPMVB200_OK;
     if (num_tiles > 0x7fffffffLL) return SPMVB200_ERR_UNSUPPORTED;
 
@@ -768,12 +781,11 @@ int launch_merge(const SpmvProblem<OffT, ValT> &p) {
     SPMV_TRY(scratch_get(p.stream, SCRATCH_CARRY_ROW, (size_t)num_tiles * sizeof(int32_t), &crow));
     SPMV_TRY(scratch_get(p.stream, SCRATCH_CARRY_VAL, (size_t)num_tiles * sizeof(ValT), &cval));
 
-    SPMV_TRY(launch_partition<OffT>(p.n_rows, p.nnz, p.Ap, kMergeTile, num_tiles + 1,
+    SPMV_TRY(launch_partition<OffT>(p.n_rows, p.nnz, p.Ap, tile_items, num_tiles + 1,
                                     static_cast<int32_t *>(coords), p.stream));
 
     // "merge_staging": 0 (default) = Aj/Ax into registers, 1 = TMA bulk copies into shared
-    // memory (kept for the ablation that decided against it; see merge_tile_reg_kernel)
-    const bool tma = option_get("merge_staging", 0) == 1;
+    // memory (kept for the ablation that decided against it; see merge_tile_reg_body)
     const int64_t carveout = option_get("merge_carveout", -1);
     LaunchCfg lc;
     if (tma) {
@@ -795,18 +807,20 @@ int launch_merge(const SpmvProblem<OffT, ValT> &p) {
                                          (const int32_t *)coords, static_cast<int32_t *>(crow),
                                          static_cast<ValT *>(cval)));
     } else {
-        constexpr bool occ8 = sizeof(OffT) == 4 && sizeof(ValT) == 4;
+        // (o32, fp32) needs the explicit occupancy bound to stay at 32 registers; (o64, fp32)
+        // gets 32 registers from ptxas unprompted and spills under the bound; fp64 needs 64
+        constexpr bool occ = sizeof(ValT) == 4 && sizeof(OffT) == 4;
         const bool has_peers = p.peers.n != 0;
-        auto kernel = has_peers ? merge_tile_reg_kernel<true, OffT, ValT>      // 40 regs, no spill
-                      : occ8    ? merge_tile_reg_kernel_occ8<false, OffT, ValT>
-                                : merge_tile_reg_kernel<false, OffT, ValT>;
+        auto kernel = has_peers ? merge_tile_reg_kernel<RB, true, OffT, ValT>      // 40 regs, no spill
+                      : occ     ? merge_tile_reg_kernel_occ8<RB, false, OffT, ValT>
+                                : merge_tile_reg_kernel<RB, false, OffT, ValT>;
         static int64_t attr_carveout = -2;
         if (attr_carveout != carveout) {
             SPMV_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                                carveout < 0 ? (int)cudaSharedmemCarveoutDefault : (int)carveout));
             attr_carveout = carveout;
         }
-        make_launch_cfg(lc, dim3((unsigned)num_tiles), dim3(kMergeBlock), 0, p.stream, p.x,
+        make_launch_cfg(lc, dim3((unsigned)num_tiles), dim3(RB), 0, p.stream, p.x,
                         (size_t)p.n_cols * sizeof(ValT));
         KernelTimerScope timed(p.stream);
         SPMV_CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, kernel, p.n_rows, p.nnz, p.Ap, p.Aj, p.Ax, p.x, p.y,
