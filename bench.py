@@ -54,7 +54,9 @@ def parse_args():
                    help="shrink the workload (R-MAT scale / rows / grid); development only")
     p.add_argument("--kind", default="auto")
     p.add_argument("--exchange", default="auto", choices=["auto", "mc", "p2p", "nccl"])
-    p.add_argument("--e2e-steps", type=int, default=10)
+    p.add_argument("--e2e-steps", type=int, default=24)
+    p.add_argument("--e2e-slots", type=int, default=3, choices=[1, 2, 3, 4],
+                   help="host-buffer calls in flight in the e2e leg (own stream + device x/y each)")
     p.add_argument("--cpu-seconds", type=float, default=15.0,
                    help="budget of the cpu_baseline leg (own arm)")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -367,10 +369,12 @@ def own_arm(args, rank, world, local_rank):
     e2e = None
     if args.e2e_steps > 0:
         mat = CsrMatrix.from_device(local)
-        xs = [torch.empty(n_cols, dtype=local.Ax.dtype, pin_memory=True) for _ in range(2)]
-        ys = [torch.empty(local.n_rows, dtype=local.Ax.dtype, pin_memory=True) for _ in range(2)]
+        ns = args.e2e_slots
+        xs = [torch.empty(n_cols, dtype=local.Ax.dtype, pin_memory=True) for _ in range(ns)]
+        ys = [torch.empty(local.n_rows, dtype=local.Ax.dtype, pin_memory=True) for _ in range(ns)]
         xs[0].copy_(it.current_x().cpu())
-        xs[1].copy_(xs[0])
+        for t in xs[1:]:
+            t.copy_(xs[0])
         xn, yn = [t.numpy() for t in xs], [t.numpy() for t in ys]
 
         def timed(fn):
@@ -388,11 +392,12 @@ def own_arm(args, rank, world, local_rank):
             mat.spmv(xn[0], yn[0], kind=args.kind)
         # one call at a time: upload, kernel, download, back to back
         dt_serial = timed(lambda: [mat.spmv(xn[0], yn[0], kind=args.kind) for _ in range(k)])
-        # the pipelined call for a sequence of right-hand sides: two slots in flight, so one
-        # step's upload overlaps the previous step's kernel and download
-        mat.spmv_many([xn[i & 1] for i in range(2)], [yn[i & 1] for i in range(2)], kind=args.kind)
-        dt = timed(lambda: mat.spmv_many([xn[i & 1] for i in range(k)], [yn[i & 1] for i in range(k)],
-                                         kind=args.kind))
+        # the pipelined call for a sequence of right-hand sides: `ns` slots in flight, so one
+        # step's upload overlaps another step's kernel and a third's download
+        mat.spmv_many([xn[i % ns] for i in range(ns)], [yn[i % ns] for i in range(ns)], kind=args.kind,
+                      slots=ns)
+        dt = timed(lambda: mat.spmv_many([xn[i % ns] for i in range(k)], [yn[i % ns] for i in range(k)],
+                                         kind=args.kind, slots=ns))
         e2e = {"value": 2.0 * nnz_total * k / dt / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": int(n_cols * xs[0].element_size()),
                "d2h_bytes_per_step": int(local.n_rows * ys[0].element_size()),
@@ -401,9 +406,9 @@ def own_arm(args, rank, world, local_rank):
                "serial_ms_per_step": dt_serial / k * 1e3,
                "api": "spmv_samples_b200.matrix.CsrMatrix.spmv_many (spmvb200_matrix_submit_host / "
                       "_wait): matrix resident (uploaded once, as reference main.cu:55-69); every "
-                      "step uploads its x from pinned host memory, runs the SpMV and downloads y; two "
-                      "steps in flight on two streams.  serial_value: CsrMatrix.spmv, one step at a "
-                      "time"}
+                      "step uploads its x from pinned host memory, runs the SpMV and downloads y; "
+                      f"{ns} steps in flight on {ns} streams.  serial_value: CsrMatrix.spmv, one step "
+                      "at a time"}
         mat.close()
 
     it.close()

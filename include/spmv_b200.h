@@ -228,11 +228,15 @@ SPMVB200_API int spmvb200_matrix_create_from_device(int offset_bits, int value_b
                                                     spmvb200_matrix_t **out);
 SPMVB200_API int spmvb200_matrix_spmv_host(spmvb200_matrix_t *m, int kind, const void *x_host,
                                            void *y_host);
-/* Pipelined form for a sequence of independent right-hand sides: two slots (0, 1), each with its
- * own stream and device x/y.  submit enqueues H2D(x) -> SpMV -> D2H(y) on the slot's stream and
- * returns; wait blocks until that slot's y_host is complete.  Alternating the slots overlaps one
- * call's upload with the other's kernel and download (both copy engines + the SMs busy).
- * x_host / y_host should be pinned, and must stay untouched until the slot has been waited on. */
+/* Pipelined form for a sequence of independent right-hand sides: SPMVB200_MAX_SLOTS slots
+ * (0 .. MAX-1), each with its own stream and device x/y (created on first use).  submit enqueues
+ * H2D(x) -> SpMV -> D2H(y) on the slot's stream and returns; wait blocks until that slot's y_host
+ * is complete.  Cycling through the slots overlaps one call's upload with another's kernel and a
+ * third's download (both copy engines + the SMs busy): a step is upload + kernel + download long,
+ * so three slots are what it takes to hide both copies behind the kernel when each copy is
+ * shorter than the kernel.  x_host / y_host should be pinned, and must stay untouched until the
+ * slot has been waited on. */
+#define SPMVB200_MAX_SLOTS 4
 SPMVB200_API int spmvb200_matrix_submit_host(spmvb200_matrix_t *m, int kind, int slot,
                                              const void *x_host, void *y_host);
 SPMVB200_API int spmvb200_matrix_wait(spmvb200_matrix_t *m, int slot);

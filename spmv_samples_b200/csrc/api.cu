@@ -233,13 +233,13 @@ void spmvb200_release_cache(void) {
 struct spmvb200_matrix {
     int offset_bits, value_bits;
     int64_t n_rows, n_cols, nnz;
-    void *Ap = nullptr, *Ax = nullptr, *x = nullptr, *y = nullptr;
+    void *Ap = nullptr, *Ax = nullptr;
     int32_t *Aj = nullptr;
-    cudaStream_t stream = nullptr;
     bool owns_csr = true;
-    // second pipeline slot (own stream and x/y buffers), created on first use
-    void *x1 = nullptr, *y1 = nullptr;
-    cudaStream_t stream1 = nullptr;
+    // pipeline slots: each has its own stream and device x/y; slot 0 exists from creation, the
+    // others are created on first use
+    void *x[SPMVB200_MAX_SLOTS] = {}, *y[SPMVB200_MAX_SLOTS] = {};
+    cudaStream_t stream[SPMVB200_MAX_SLOTS] = {};
 };
 
 namespace spmvb200 {
@@ -298,9 +298,9 @@ int spmvb200_matrix_create_from_device(int offset_bits, int value_bits, int64_t 
     m->Ax = const_cast<void *>(Ax_dev);
     const size_t vb = value_bits / 8;
     cudaError_t e;
-    if ((e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaMalloc(&m->x, (size_t)(n_cols ? n_cols : 1) * vb)) != cudaSuccess ||
-        (e = cudaMalloc(&m->y, (size_t)(n_rows ? n_rows : 1) * vb)) != cudaSuccess) {
+    if ((e = cudaStreamCreateWithFlags(&m->stream[0], cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaMalloc(&m->x[0], (size_t)(n_cols ? n_cols : 1) * vb)) != cudaSuccess ||
+        (e = cudaMalloc(&m->y[0], (size_t)(n_rows ? n_rows : 1) * vb)) != cudaSuccess) {
         record_cuda_error(e, "matrix_create_from_device", __FILE__, __LINE__);
         spmvb200_matrix_destroy(m);
         return SPMVB200_ERR_CUDA;
@@ -334,34 +334,33 @@ int spmvb200_matrix_create(int offset_bits, int value_bits, int64_t n_rows, int6
         return SPMVB200_ERR_CUDA;
     };
     cudaError_t e;
-    if ((e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+    if ((e = cudaStreamCreateWithFlags(&m->stream[0], cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
     if ((e = cudaMalloc(&m->Ap, (size_t)(n_rows + 1) * ob)) != cudaSuccess) return fail(e, "cudaMalloc Ap");
     if ((e = cudaMalloc((void **)&m->Aj, (size_t)(nnz ? nnz : 1) * 4)) != cudaSuccess) return fail(e, "cudaMalloc Aj");
     if ((e = cudaMalloc(&m->Ax, (size_t)(nnz ? nnz : 1) * vb)) != cudaSuccess) return fail(e, "cudaMalloc Ax");
-    if ((e = cudaMalloc(&m->x, (size_t)(n_cols ? n_cols : 1) * vb)) != cudaSuccess) return fail(e, "cudaMalloc x");
-    if ((e = cudaMalloc(&m->y, (size_t)(n_rows ? n_rows : 1) * vb)) != cudaSuccess) return fail(e, "cudaMalloc y");
-    if ((e = cudaMemcpyAsync(m->Ap, Ap_host, (size_t)(n_rows + 1) * ob, cudaMemcpyHostToDevice, m->stream)) != cudaSuccess) return fail(e, "H2D Ap");
+    if ((e = cudaMalloc(&m->x[0], (size_t)(n_cols ? n_cols : 1) * vb)) != cudaSuccess) return fail(e, "cudaMalloc x");
+    if ((e = cudaMalloc(&m->y[0], (size_t)(n_rows ? n_rows : 1) * vb)) != cudaSuccess) return fail(e, "cudaMalloc y");
+    if ((e = cudaMemcpyAsync(m->Ap, Ap_host, (size_t)(n_rows + 1) * ob, cudaMemcpyHostToDevice, m->stream[0])) != cudaSuccess) return fail(e, "H2D Ap");
     if (nnz > 0) {
-        if ((e = cudaMemcpyAsync(m->Aj, Aj_host, (size_t)nnz * 4, cudaMemcpyHostToDevice, m->stream)) != cudaSuccess) return fail(e, "H2D Aj");
-        if ((e = cudaMemcpyAsync(m->Ax, Ax_host, (size_t)nnz * vb, cudaMemcpyHostToDevice, m->stream)) != cudaSuccess) return fail(e, "H2D Ax");
+        if ((e = cudaMemcpyAsync(m->Aj, Aj_host, (size_t)nnz * 4, cudaMemcpyHostToDevice, m->stream[0])) != cudaSuccess) return fail(e, "H2D Aj");
+        if ((e = cudaMemcpyAsync(m->Ax, Ax_host, (size_t)nnz * vb, cudaMemcpyHostToDevice, m->stream[0])) != cudaSuccess) return fail(e, "H2D Ax");
     }
-    if ((e = cudaStreamSynchronize(m->stream)) != cudaSuccess) return fail(e, "sync");
+    if ((e = cudaStreamSynchronize(m->stream[0])) != cudaSuccess) return fail(e, "sync");
     *out = m;
     return SPMVB200_OK;
 }
 
 int spmvb200_matrix_submit_host(spmvb200_matrix_t *m, int kind, int slot, const void *x_host,
                                 void *y_host) {
-    if (!m || slot < 0 || slot > 1 || (!x_host && m->n_cols > 0) || (!y_host && m->n_rows > 0))
+    if (!m || slot < 0 || slot >= SPMVB200_MAX_SLOTS || (!x_host && m->n_cols > 0) ||
+        (!y_host && m->n_rows > 0))
         return SPMVB200_ERR_INVALID;
     const size_t vb = m->value_bits / 8;
-    if (slot == 1 && !m->stream1) {
-        SPMV_CUDA_TRY(cudaStreamCreateWithFlags(&m->stream1, cudaStreamNonBlocking));
-        SPMV_CUDA_TRY(cudaMalloc(&m->x1, (size_t)(m->n_cols ? m->n_cols : 1) * vb));
-        SPMV_CUDA_TRY(cudaMalloc(&m->y1, (size_t)(m->n_rows ? m->n_rows : 1) * vb));
-    }
-    cudaStream_t st = slot ? m->stream1 : m->stream;
-    void *dx = slot ? m->x1 : m->x, *dy = slot ? m->y1 : m->y;
+    if (!m->stream[slot]) SPMV_CUDA_TRY(cudaStreamCreateWithFlags(&m->stream[slot], cudaStreamNonBlocking));
+    if (!m->x[slot]) SPMV_CUDA_TRY(cudaMalloc(&m->x[slot], (size_t)(m->n_cols ? m->n_cols : 1) * vb));
+    if (!m->y[slot]) SPMV_CUDA_TRY(cudaMalloc(&m->y[slot], (size_t)(m->n_rows ? m->n_rows : 1) * vb));
+    cudaStream_t st = m->stream[slot];
+    void *dx = m->x[slot], *dy = m->y[slot];
     if (m->n_cols > 0)
         SPMV_CUDA_TRY(cudaMemcpyAsync(dx, x_host, (size_t)m->n_cols * vb, cudaMemcpyHostToDevice, st));
     spmvb200_args_t a;
@@ -387,9 +386,8 @@ int spmvb200_matrix_submit_host(spmvb200_matrix_t *m, int kind, int slot, const 
 }
 
 int spmvb200_matrix_wait(spmvb200_matrix_t *m, int slot) {
-    if (!m || slot < 0 || slot > 1) return SPMVB200_ERR_INVALID;
-    cudaStream_t st = slot ? m->stream1 : m->stream;
-    if (st) SPMV_CUDA_TRY(cudaStreamSynchronize(st));
+    if (!m || slot < 0 || slot >= SPMVB200_MAX_SLOTS) return SPMVB200_ERR_INVALID;
+    if (m->stream[slot]) SPMV_CUDA_TRY(cudaStreamSynchronize(m->stream[slot]));
     return SPMVB200_OK;
 }
 
@@ -400,19 +398,18 @@ int spmvb200_matrix_spmv_host(spmvb200_matrix_t *m, int kind, const void *x_host
 
 void spmvb200_matrix_destroy(spmvb200_matrix_t *m) {
     if (!m) return;
-    if (m->stream) cudaStreamSynchronize(m->stream);
+    for (cudaStream_t st : m->stream)
+        if (st) cudaStreamSynchronize(st);
     if (m->owns_csr) {
         if (m->Ap) cudaFree(m->Ap);
         if (m->Aj) cudaFree(m->Aj);
         if (m->Ax) cudaFree(m->Ax);
     }
-    if (m->stream1) cudaStreamSynchronize(m->stream1);
-    if (m->x) cudaFree(m->x);
-    if (m->y) cudaFree(m->y);
-    if (m->x1) cudaFree(m->x1);
-    if (m->y1) cudaFree(m->y1);
-    if (m->stream) cudaStreamDestroy(m->stream);
-    if (m->stream1) cudaStreamDestroy(m->stream1);
+    for (int k = 0; k < SPMVB200_MAX_SLOTS; ++k) {
+        if (m->x[k]) cudaFree(m->x[k]);
+        if (m->y[k]) cudaFree(m->y[k]);
+        if (m->stream[k]) cudaStreamDestroy(m->stream[k]);
+    }
     delete m;
 }
 

@@ -15,6 +15,9 @@ from . import _lib
 from .spmv import KIND_IDS, SpMVKindError
 
 
+MAX_SLOTS = 4  # SPMVB200_MAX_SLOTS in include/spmv_b200.h
+
+
 class CsrMatrix:
     def __init__(self, n_rows: int, n_cols: int, Ap: np.ndarray, Aj: np.ndarray, Ax: np.ndarray):
         if Ap.dtype not in (np.int32, np.int64):
@@ -67,7 +70,7 @@ class CsrMatrix:
         return y
 
     def submit(self, slot: int, x: np.ndarray, y: np.ndarray, kind: str = "auto") -> None:
-        """Asynchronous y = A @ x on pipeline slot 0 or 1 (own stream, own device buffers): the
+        """Asynchronous y = A @ x on pipeline slot 0..MAX_SLOTS-1 (own stream, own device buffers): the
         upload, the kernel and the download are enqueued and the call returns.  x and y should be
         pinned host arrays and must not be touched until wait(slot)."""
         if kind not in KIND_IDS:
@@ -82,14 +85,19 @@ class CsrMatrix:
     def wait(self, slot: int) -> None:
         _lib.check(_lib.lib().spmvb200_matrix_wait(self._h, int(slot)), "spmvb200_matrix_wait")
 
-    def spmv_many(self, xs, ys, kind: str = "auto") -> None:
-        """ys[i] = A @ xs[i] for a sequence of independent right-hand sides, two in flight."""
+    def spmv_many(self, xs, ys, kind: str = "auto", slots: int = 3) -> None:
+        """ys[i] = A @ xs[i] for a sequence of independent right-hand sides, `slots` in flight
+        (3: one uploading, one in the kernel, one downloading)."""
+        if not 1 <= slots <= MAX_SLOTS:
+            raise ValueError(f"slots must be in 1..{MAX_SLOTS}")
+        n = 0
         for i, (x, y) in enumerate(zip(xs, ys)):
-            if i >= 2:
-                self.wait(i & 1)
-            self.submit(i & 1, x, y, kind)
-        self.wait(0)
-        self.wait(1)
+            if i >= slots:
+                self.wait(i % slots)
+            self.submit(i % slots, x, y, kind)
+            n = i + 1
+        for s in range(min(n, slots)):
+            self.wait(s)
 
     def close(self):
         if getattr(self, "_h", None):

@@ -156,16 +156,19 @@ def test_two_gpu_sharded_iteration_matches_single_gpu(tmp_path, exchange):
     assert np.linalg.norm(x0.astype(np.float64) - ref) <= 1e-5 * np.linalg.norm(ref)
 
 
-def test_pipelined_host_buffer_api_matches_serial():
+@pytest.mark.parametrize("slots", [1, 2, 3, 4])
+def test_pipelined_host_buffer_api_matches_serial(slots):
     from spmv_samples_b200 import generate as gen
     from spmv_samples_b200.matrix import CsrMatrix
     m = gen.rmat(15, 16, 3)
     Ap, Aj, Ax = g.rmat(15, 16, 3)
     mat = CsrMatrix.from_device(m)
-    xs = [torch.from_numpy(g.gen_x(100 + i, m.n_cols)).pin_memory().numpy() for i in range(5)]
-    ys = [torch.empty(m.n_rows, dtype=torch.float32).pin_memory().numpy() for _ in range(5)]
-    mat.spmv_many(xs, ys, kind="auto")
+    xs = [torch.from_numpy(g.gen_x(100 + i, m.n_cols)).pin_memory().numpy() for i in range(7)]
+    ys = [torch.empty(m.n_rows, dtype=torch.float32).pin_memory().numpy() for _ in range(7)]
+    mat.spmv_many(xs, ys, kind="auto", slots=slots)
     for x, y in zip(xs, ys):
         assert np.array_equal(y, mat.spmv(x, kind="auto"))          # same kernels, same bits
         assert np.all(np.abs(y - cpu.spmv_fp64(Ap, Aj, Ax, x)) <= 1e-5 * cpu.abs_scale(Ap, Aj, Ax, x))
+    with pytest.raises(ValueError):
+        mat.spmv_many(xs, ys, slots=5)
     mat.close()
