@@ -54,6 +54,11 @@ def parse_args():
                    help="shrink the workload (R-MAT scale / rows / grid); development only")
     p.add_argument("--kind", default="auto")
     p.add_argument("--exchange", default="auto", choices=["auto", "mc", "p2p", "nccl"])
+    p.add_argument("--row-weight", default="1/1",
+                   help="multi-GPU row split: cost of a row in nonzeros, num/den (1/1 = merge path)")
+    p.add_argument("--rebalance", type=int, default=2,
+                   help="multi-GPU: rounds of re-splitting the rows from measured per-rank local "
+                        "step times (partition + tile kernel + fix-up + norm) before the timed region")
     p.add_argument("--e2e-steps", type=int, default=24)
     p.add_argument("--e2e-slots", type=int, default=3, choices=[1, 2, 3, 4],
                    help="host-buffer calls in flight in the e2e leg (own stream + device x/y each)")
@@ -283,7 +288,9 @@ def own_arm(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path "
                          "(use --impl reference for the CPU baseline)")
     _lib.lib()
-    spmv.set_option("time_main_kernel", 1)
+    # diagnostics only (the contract line needs both): BENCH_NO_KTIMER=1 leaves the per-kernel
+    # event timer off, BENCH_NO_SAMPLER=1 the NVML clock sampler
+    spmv.set_option("time_main_kernel", 0 if os.environ.get("BENCH_NO_KTIMER") else 1)
     peak, peak_src = measured_peak()
 
     # ---- the matrix: every rank builds the global CSR on its own GPU, keeps its rows
@@ -294,7 +301,8 @@ def own_arm(args, rank, world, local_rank):
         raise SystemExit("power iteration needs a square matrix")
     alg_bytes_total = gm.algorithmic_bytes()
     stats = spmv.row_stats(gm.Ap, nnz=gm.nnz)
-    shard = shard_rows(gm, rank, world)
+    weight = tuple(int(v) for v in args.row_weight.split("/"))
+    shard = shard_rows(gm, rank, world, weight=weight)
     x_for_cpu = generate.gen_x(n_cols, SEED, gm.Ax.dtype) if (rank == 0 and world == 1) else None
     cpu_info = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -306,14 +314,21 @@ def own_arm(args, rank, world, local_rank):
         except Exception as e:  # the baseline is reported, never required
             cpu_info = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
                         "sample": f"failed: {e}"}
-    if world > 1:
-        del gm
-        torch.cuda.empty_cache()
     torch.cuda.synchronize()
     t_gen = time.perf_counter() - t_gen
-    local = shard.csr
 
     it = PowerIteration(shard, n, kind=args.kind, exchange=args.exchange)
+    rebalance_log = []
+    if world > 1:
+        for _ in range(args.rebalance):
+            for _ in range(3):
+                it.step()
+            times, rb = it.rebalance(gm, steps=5, weight=weight)
+            rebalance_log.append({"local_ms_before": [round(v, 4) for v in times], "row_bounds": rb})
+        shard = it.shard
+        del gm
+        torch.cuda.empty_cache()
+    local = shard.csr
 
     def barrier():
         torch.cuda.synchronize()
@@ -330,6 +345,8 @@ def own_arm(args, rank, world, local_rank):
     _lib.lib().spmvb200_main_kernel_time(ctypes.byref(d_ms), ctypes.byref(d_n))   # reset the kernel timer
     launches0 = spmv.launch_count()
     sampler = ClockSampler(physical_gpu_index(local_rank))
+    if os.environ.get("BENCH_NO_SAMPLER"):
+        sampler.ok = False
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -427,7 +444,9 @@ def own_arm(args, rank, world, local_rank):
                 "step": "one power-iteration SpMV (x <- A x / ||A x||) over the whole matrix, "
                         "incl. x exchange and norm",
                 "kind": args.kind, "selected_kernel": kind_names.get(stats["chosen_kind"]),
-                "exchange": it.exchange, "exchange_note": getattr(it, "exchange_note", ""), "parallelism": f"row-sharded x{world} (merge-path nnz split)",
+                "exchange": it.exchange, "exchange_note": getattr(it, "exchange_note", ""), "parallelism": f"row-sharded x{world} (merge-path nnz split, row weight {args.row_weight}"
+                                + (f", re-split {args.rebalance}x from measured per-rank local step times)" if world > 1 and args.rebalance else ")"),
+                "rebalance": rebalance_log,
                 "l2": "inputs larger than L2 (no flush needed)" if alg_bytes_total > 4 * 126e6
                       else "inputs smaller than L2: steps run back to back, L2-warm",
                 "generation_s": t_gen, "eigen_estimate": eig,

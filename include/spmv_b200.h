@@ -189,6 +189,19 @@ SPMVB200_API int spmvb200_row_split_o32(int32_t n_rows, int32_t nnz, const int32
 SPMVB200_API int spmvb200_row_split_o64(int32_t n_rows, int64_t nnz, const int64_t *Ap, int parts,
                                         int64_t *row_bounds, spmvb200_stream_t stream);
 
+/* Weighted form of the same search, for splits that weigh a row differently from a nonzero or
+ * that are re-balanced from measured shard times (spmv_samples_b200/dist.py): with
+ * f(r) = w_den*Ap[r] + w_num*r the cost of the first r rows (w_num/w_den = cost of a row in
+ * nonzeros; 1/1 is the merge path above), rows_out[k] = max{ r in [0, n_rows] : f(r) <= targets[k] }.
+ * targets / rows_out are HOST arrays of n_targets int64; 0 <= w_num, 1 <= w_den, both <= 2^20.
+ * Synchronises. */
+SPMVB200_API int spmvb200_rows_at_cost_o32(int32_t n_rows, const int32_t *Ap, int64_t w_num,
+                                           int64_t w_den, int n_targets, const int64_t *targets,
+                                           int64_t *rows_out, spmvb200_stream_t stream);
+SPMVB200_API int spmvb200_rows_at_cost_o64(int32_t n_rows, const int64_t *Ap, int64_t w_num,
+                                           int64_t w_den, int n_targets, const int64_t *targets,
+                                           int64_t *rows_out, spmvb200_stream_t stream);
+
 /* ---- row statistics + selector --------------------------------------------------------- */
 typedef struct {
     int64_t n_rows;

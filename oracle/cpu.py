@@ -195,6 +195,17 @@ def row_split(Ap, parts: int) -> np.ndarray:
     return out
 
 
+def rows_at_cost(Ap, targets, weight=(1, 1)) -> np.ndarray:
+    """Weighted split search, restated with numpy: f(r) = w_den*Ap[r] + w_num*r; for each target
+    the largest r in [0, n_rows] with f(r) <= target.  With weight (1, 1) and targets
+    floor(g*(n_rows+nnz)/P) this is row_split above (thread_search.cuh:16-49 returns the first p
+    with f(p+1) > d)."""
+    f = int(weight[1]) * np.asarray(Ap, dtype=np.int64) + int(weight[0]) * np.arange(Ap.shape[0], dtype=np.int64)
+    t = np.asarray(targets, dtype=np.int64)
+    # f is non-decreasing; side="right" counts the entries <= target, f[0] = 0 is always one
+    return np.searchsorted(f, t, side="right").astype(np.int64) - 1
+
+
 # ------------------------------------------------------------------- COO -> CSR
 def coo_to_csr(n_rows: int, rows, cols, vals, offset_dtype=np.int32):
     rows = np.ascontiguousarray(rows, dtype=np.int32)

@@ -101,6 +101,10 @@ def lib() -> C.CDLL:
                                          C.POINTER(C.c_int64), C.c_void_p]
     L.spmvb200_row_split_o64.argtypes = [C.c_int32, C.c_int64, C.c_void_p, C.c_int,
                                          C.POINTER(C.c_int64), C.c_void_p]
+    for tag in ("o32", "o64"):
+        getattr(L, f"spmvb200_rows_at_cost_{tag}").argtypes = [
+            C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.POINTER(C.c_int64),
+            C.POINTER(C.c_int64), C.c_void_p]
     L.spmvb200_gen_uniform_pm1.argtypes = [C.c_int, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int64,
                                            C.c_void_p, C.c_void_p]
     L.spmvb200_gen_lap2d.argtypes = [C.c_int, C.c_int, C.c_int32, C.c_void_p, C.c_void_p,

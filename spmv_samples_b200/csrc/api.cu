@@ -167,6 +167,27 @@ int64_t spmvb200_merge_tile_items(int offset_bits, int) { return merge_tile_item
 
 }  // extern "C"
 
+namespace spmvb200 {
+// Weighted variant of the same search: the cost of the first r rows is
+// f(r) = w_den * Ap[r] + w_num * r (a row costs w_num / w_den of a nonzero; 1/1 is the merge
+// path), and out[k] = max{ r in [0, n_rows] : f(r) <= targets[k] }.  One thread per target.
+template <typename OffT>
+__global__ void rows_at_cost_kernel(int32_t n_rows, const OffT *__restrict__ Ap, int64_t w_num,
+                                    int64_t w_den, int n_targets, const int64_t *__restrict__ targets,
+                                    int64_t *__restrict__ rows_out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_targets) return;
+    const int64_t d = targets[k];
+    int64_t lo = 0, hi = n_rows;  // f(0) = 0 <= d for every d >= 0
+    while (lo < hi) {
+        const int64_t mid = lo + ((hi - lo + 1) >> 1);
+        const int64_t f = w_den * (int64_t)__ldg(Ap + mid) + w_num * mid;
+        if (f <= d) lo = mid; else hi = mid - 1;
+    }
+    rows_out[k] = lo;
+}
+}  // namespace spmvb200
+
 namespace {
 // diagonals floor(g*total/parts) are not an arithmetic progression in general, so the split
 // reuses the partition kernel once per boundary with tile_items = that diagonal, n_coords = 2
@@ -198,9 +219,51 @@ int row_split_impl(int32_t n_rows, OffT nnz, const OffT *Ap, int parts, int64_t 
     row_bounds[parts] = n_rows;
     return SPMVB200_OK;
 }
+
+template <typename OffT>
+int rows_at_cost_impl(int32_t n_rows, const OffT *Ap, int64_t w_num, int64_t w_den, int n_targets,
+                      const int64_t *targets, int64_t *rows_out, cudaStream_t stream) {
+    if (n_rows < 0 || (!Ap && n_rows > 0) || w_num < 0 || w_den < 1 || n_targets < 0 ||
+        (n_targets > 0 && (!targets || !rows_out)))
+        return SPMVB200_ERR_INVALID;
+    // f must stay inside int64: Ap[r] < 2^63 / (2 * w_den) is implied by these bounds
+    if (w_num > (1 << 20) || w_den > (1 << 20)) return SPMVB200_ERR_UNSUPPORTED;
+    if (n_targets == 0) return SPMVB200_OK;
+    for (int k = 0; k < n_targets; ++k)
+        if (targets[k] < 0) return SPMVB200_ERR_INVALID;
+    if (n_rows == 0) {
+        for (int k = 0; k < n_targets; ++k) rows_out[k] = 0;
+        return SPMVB200_OK;
+    }
+    void *dbuf = nullptr;
+    SPMV_TRY(scratch_get(stream, SCRATCH_MISC, (size_t)n_targets * 2 * sizeof(int64_t), &dbuf));
+    int64_t *d_t = static_cast<int64_t *>(dbuf), *d_r = d_t + n_targets;
+    SPMV_CUDA_TRY(cudaMemcpyAsync(d_t, targets, (size_t)n_targets * sizeof(int64_t), cudaMemcpyHostToDevice,
+                                  stream));
+    spmvb200::rows_at_cost_kernel<OffT><<<(n_targets + 127) / 128, 128, 0, stream>>>(n_rows, Ap, w_num, w_den,
+                                                                           n_targets, d_t, d_r);
+    SPMV_LAUNCH_CHECK();
+    SPMV_CUDA_TRY(cudaMemcpyAsync(rows_out, d_r, (size_t)n_targets * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                                  stream));
+    SPMV_CUDA_TRY(cudaStreamSynchronize(stream));
+    return SPMVB200_OK;
+}
 }  // namespace
 
 extern "C" {
+
+int spmvb200_rows_at_cost_o32(int32_t n_rows, const int32_t *Ap, int64_t w_num, int64_t w_den,
+                              int n_targets, const int64_t *targets, int64_t *rows_out,
+                              spmvb200_stream_t stream) {
+    return rows_at_cost_impl<int32_t>(n_rows, Ap, w_num, w_den, n_targets, targets, rows_out,
+                                      static_cast<cudaStream_t>(stream));
+}
+int spmvb200_rows_at_cost_o64(int32_t n_rows, const int64_t *Ap, int64_t w_num, int64_t w_den,
+                              int n_targets, const int64_t *targets, int64_t *rows_out,
+                              spmvb200_stream_t stream) {
+    return rows_at_cost_impl<int64_t>(n_rows, Ap, w_num, w_den, n_targets, targets, rows_out,
+                                      static_cast<cudaStream_t>(stream));
+}
 
 int spmvb200_row_split_o32(int32_t n_rows, int32_t nnz, const int32_t *Ap, int parts,
                            int64_t *row_bounds, spmvb200_stream_t stream) {

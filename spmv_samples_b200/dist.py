@@ -84,11 +84,20 @@ class Shard:
     csr: generate.Csr  # local rows, offsets rebased to 0, n_cols = global
 
 
-def shard_rows(global_csr: generate.Csr, rank: int, world: int, value_seed=None) -> Shard:
+def shard_rows(global_csr: generate.Csr, rank: int, world: int, value_seed=None, row_bounds=None,
+               weight=(1, 1)) -> Shard:
     """Cut rank's rows out of a global CSR held on this device.  Boundaries come from the
-    device merge-path search (bit-exact against oracle.cpu.row_split in the tests)."""
-    rb = spmv_mod.row_split(global_csr.Ap, world, nnz=global_csr.nnz) if world > 1 else \
-        [0, global_csr.n_rows]
+    device merge-path search (bit-exact against oracle.cpu.row_split in the tests), with a row
+    weighing `weight` = (num, den) nonzeros, or are given (row_bounds, world + 1 values)."""
+    if row_bounds is not None:
+        rb = [int(v) for v in row_bounds]
+        if len(rb) != world + 1 or rb[0] != 0 or rb[-1] != global_csr.n_rows or \
+                any(a > b for a, b in zip(rb, rb[1:])):
+            raise ValueError("row_bounds must be world + 1 non-decreasing rows from 0 to n_rows")
+    elif world > 1:
+        rb = spmv_mod.row_split(global_csr.Ap, world, nnz=global_csr.nnz, weight=weight)
+    else:
+        rb = [0, global_csr.n_rows]
     r0, r1 = rb[rank], rb[rank + 1]
     k0, k1 = int(global_csr.Ap[r0].item()), int(global_csr.Ap[r1].item())
     if world == 1:
@@ -100,6 +109,19 @@ def shard_rows(global_csr: generate.Csr, rank: int, world: int, value_seed=None)
         local = generate.Csr(r1 - r0, global_csr.n_cols, k1 - k0, Ap, Aj, Ax,
                              f"{global_csr.name}[rank {rank}/{world}]")
     return Shard(rank, world, r0, r1, k0, k1, rb, local)
+
+
+def rebalanced_bounds(global_csr: generate.Csr, row_bounds, times, weight=(1, 1)):
+    """Row boundaries for a re-split from measured per-shard times: the cost f(r) = den*Ap[r] + num*r
+    of every current boundary, the equal-time quantiles of the piecewise-linear time-over-cost
+    curve (spmv.rebalance_targets), and the device search for the rows at those costs."""
+    wn, wd = int(weight[0]), int(weight[1])
+    idx = torch.tensor([int(b) for b in row_bounds], dtype=torch.int64, device=global_csr.Ap.device)
+    ap = [int(v) for v in global_csr.Ap[idx].tolist()]
+    cost = [wd * a + wn * int(b) for a, b in zip(ap, row_bounds)]
+    targets = spmv_mod.rebalance_targets(cost, times)
+    rows = spmv_mod.rows_at_cost(global_csr.Ap, targets, (wn, wd))
+    return [0] + rows + [global_csr.n_rows]
 
 
 class PowerIteration:
@@ -158,6 +180,7 @@ class PowerIteration:
             dev = "cpu"
             if self.exchange != "none":
                 self.exchange = "nccl"  # collectives only on the host
+        self._local_events = None   # set by shard_local_ms: (start, stop) events per step
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
         self.alpha = torch.ones(1, dtype=self.dtype, device=dev)
         self.step_no = 0
@@ -221,6 +244,10 @@ class PowerIteration:
         else:
             peers = []
         if self.host_ops is None:
+            if self._local_events is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                self._local_events.append(ev)
+                ev[0].record()
             spmv_mod.spmv_ex(self.kind, m.Ap, m.Aj, m.Ax, x, y, n_cols=self.n, alpha_dev=self.alpha,
                              y_peers=peers, multicast=self.exchange == "mc")
             if self.step_no == 0 and self.exchange in ("p2p", "mc"):
@@ -233,6 +260,8 @@ class PowerIteration:
             st = L.spmvb200_sum_squares(self.vbits, y.numel(), y.data_ptr(), self.sumsq.data_ptr(),
                                         torch.cuda.current_stream().cuda_stream)
             _lib.check(st, "spmvb200_sum_squares")
+            if self._local_events is not None:
+                self._local_events[-1][1].record()
         else:
             self.host_ops.spmv(m, x, y, self.alpha)
             self.sumsq[0] = (y.double() ** 2).sum()
@@ -255,6 +284,43 @@ class PowerIteration:
             s2 = float(self.sumsq[0])
             self.alpha[0] = 1.0 / (s2 ** 0.5) if s2 > 0 else 1.0
         self.step_no += 1
+
+    # ------------------------------------------------------------------ re-balancing
+    def set_shard(self, shard: Shard):
+        """Continue with another row split of the same matrix (same ranks, same x replicas);
+        the iteration restarts from x0."""
+        if shard.world != self.world or shard.rank != self.rank or shard.csr.n_cols != self.n:
+            raise ValueError("set_shard: the new shard must belong to the same matrix and rank")
+        self.shard = shard
+        self.reset()
+
+    def shard_local_ms(self, steps: int = 5):
+        """Mean duration of this rank's local part of a step -- everything between the step
+        barriers that does not wait for a peer: partition, tile kernel, carry fix-up, sum of
+        squares -- over `steps` steps, for every rank (the same list on all ranks).  CUDA events
+        on the stream the step runs on."""
+        torch.cuda.synchronize()
+        self._local_events = []
+        try:
+            for _ in range(steps):
+                self.step()
+            torch.cuda.synchronize()
+            ms = sum(a.elapsed_time(b) for a, b in self._local_events) / max(len(self._local_events), 1)
+        finally:
+            self._local_events = None
+        t = torch.zeros(self.world, dtype=torch.float64, device="cuda")
+        t[self.rank] = ms
+        if self.world > 1:
+            self.dist.all_reduce(t, group=self.group)
+        return [float(v) for v in t.tolist()]
+
+    def rebalance(self, global_csr: generate.Csr, steps: int = 5, weight=(1, 1)):
+        """Measure every rank's local step time on the current split, move the row boundaries to
+        the equal-time quantiles, re-shard and restart.  Returns (times, new row bounds)."""
+        times = self.shard_local_ms(steps)
+        rb = rebalanced_bounds(global_csr, self.shard.row_bounds, times, weight)
+        self.set_shard(shard_rows(global_csr, self.rank, self.world, row_bounds=rb))
+        return times, rb
 
     def current_x(self) -> torch.Tensor:
         """The latest iterate, not yet scaled by alpha (= 1 / its norm)."""

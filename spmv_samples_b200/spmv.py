@@ -185,12 +185,64 @@ def merge_path_partition(Ap, tile_items=None, stream=None):
     return out
 
 
-def row_split(Ap, parts: int, nnz=None, stream=None):
-    """nnz-balanced row boundaries (list of parts+1 ints) from the device merge-path search."""
+def rows_at_cost(Ap, targets, weight=(1, 1), stream=None):
+    """For each target t: the largest r with f(r) = w_den*Ap[r] + w_num*r <= t, where
+    weight = (w_num, w_den) is the cost of a row in nonzeros ((1, 1): the merge path)."""
+    L = _lib.lib()
+    n_rows = Ap.numel() - 1
+    n = len(targets)
+    t = (C.c_int64 * max(n, 1))(*[int(v) for v in targets])
+    out = (C.c_int64 * max(n, 1))()
+    fn = getattr(L, f"spmvb200_rows_at_cost_{_OFF[Ap.dtype][0]}")
+    with torch.cuda.device(Ap.device):
+        st = fn(n_rows, _ptr(Ap), int(weight[0]), int(weight[1]), n, t, out, _stream_ptr(stream))
+    _lib.check(st, "spmvb200_rows_at_cost")
+    return [int(out[k]) for k in range(n)]
+
+
+def split_targets(total_cost: int, parts: int):
+    """Equal-cost targets floor(g * total / parts), g = 1 .. parts-1 (exact integers)."""
+    return [(g * int(total_cost)) // parts for g in range(1, parts)]
+
+
+def rebalance_targets(cost_bounds, times):
+    """Targets for a re-split from measured shard times.  cost_bounds[g] = f(row_bounds[g]) of the
+    current split (parts+1 values), times[g] its measured time.  Time is taken as uniform in cost
+    inside a shard, and the new boundaries are put at the equal-time quantiles of that
+    piecewise-linear curve.  Integer arithmetic on times quantised to 1/65536 of their sum, so
+    every rank computes the same targets from the same inputs."""
+    parts = len(times)
+    tot = float(sum(times))
+    if parts < 2 or tot <= 0:
+        return [int(c) for c in cost_bounds[1:-1]]
+    q = [max(1, int(round(65536.0 * float(t) / tot))) for t in times]
+    qs = sum(q)
+    cum = [0]
+    for v in q:
+        cum.append(cum[-1] + v)
+    out = []
+    for k in range(1, parts):
+        want = k * qs  # compared against cum[g] * parts
+        g = 0
+        while g + 1 < parts and cum[g + 1] * parts <= want:
+            g += 1
+        c0, c1 = int(cost_bounds[g]), int(cost_bounds[g + 1])
+        out.append(c0 + ((c1 - c0) * (want - cum[g] * parts)) // (q[g] * parts))
+    return out
+
+
+def row_split(Ap, parts: int, nnz=None, stream=None, weight=(1, 1)):
+    """nnz-balanced row boundaries (list of parts+1 ints) from the device merge-path search.
+    weight = (w_num, w_den): cost of a row relative to a nonzero; (1, 1) is the merge path of
+    SURVEY.md 8(e) and goes through spmvb200_row_split_*, any other weight through
+    spmvb200_rows_at_cost_* on the equal-cost targets."""
     L = _lib.lib()
     n_rows = Ap.numel() - 1
     if nnz is None:
         nnz = int(Ap[-1].item())
+    if tuple(weight) != (1, 1):
+        total = int(weight[1]) * int(nnz) + int(weight[0]) * n_rows
+        return [0] + rows_at_cost(Ap, split_targets(total, parts), weight, stream) + [n_rows]
     out = (C.c_int64 * (parts + 1))()
     fn = getattr(L, f"spmvb200_row_split_{_OFF[Ap.dtype][0]}")
     with torch.cuda.device(Ap.device):

@@ -100,3 +100,42 @@ def test_power_iteration_refuses_to_run_without_cuda_or_hook():
     Ap, Aj, Ax = g.rmat(6, 4, 1)
     with pytest.raises(RuntimeError, match="no CPU path"):
         PowerIteration(make_shard(Ap, Aj, Ax, 0, 1), Ap.shape[0] - 1)
+
+
+# ------------------------------------------------------------------ weighted / re-balanced split
+def test_weighted_split_restatement_is_the_merge_path_at_weight_one():
+    from oracle import cpu, generators as g
+    from spmv_samples_b200 import spmv
+    for Ap in (g.rmat(11, 16, 3, offset_dtype=np.int64)[0], g.ragged(2000, 2000, 7.0, 2)[0],
+               g.lap2d(20)[0]):
+        n_rows, nnz = Ap.shape[0] - 1, int(Ap[-1])
+        for parts in (2, 3, 5, 8):
+            t = spmv.split_targets(n_rows + nnz, parts)
+            assert [0] + cpu.rows_at_cost(Ap, t, (1, 1)).tolist() + [n_rows] == cpu.row_split(Ap, parts).tolist()
+        # weight 0: pure nonzero balance, every shard within one row of nnz / parts
+        t = spmv.split_targets(nnz, 4)
+        rb = [0] + cpu.rows_at_cost(Ap, t, (0, 1)).tolist() + [n_rows]
+        longest = int(np.diff(Ap).max())
+        for q in range(4):
+            assert abs(int(Ap[rb[q + 1]] - Ap[rb[q]]) - nnz / 4) <= longest + 1
+
+
+def test_rebalance_targets_moves_boundaries_towards_equal_time():
+    from spmv_samples_b200 import spmv
+    cost = [0, 1000, 2000, 3000, 4000]
+    # equal times: nothing moves
+    assert spmv.rebalance_targets(cost, [1.0, 1.0, 1.0, 1.0]) == [1000, 2000, 3000]
+    # shard 0 took twice as long as the others: it must shrink, the targets stay ordered
+    t = spmv.rebalance_targets(cost, [2.0, 1.0, 1.0, 1.0])
+    assert t[0] < 1000 and t == sorted(t) and all(0 <= v <= 4000 for v in t)
+    assert abs(t[0] - 625) <= 1          # 5/4 time units per shard -> 1.25 / 2 of shard 0's cost
+    # a model where time really is piecewise uniform in cost is balanced in one round
+    dens = [2.0, 1.0, 1.0, 1.0]
+    def shard_time(lo, hi):
+        return sum(dens[g] * max(0, min(hi, cost[g + 1]) - max(lo, cost[g])) / 1000.0 for g in range(4))
+    b = [0] + t + [4000]
+    times = [shard_time(b[q], b[q + 1]) for q in range(4)]
+    assert max(times) - min(times) <= 0.01 * max(times)
+    # degenerate inputs
+    assert spmv.rebalance_targets([0, 10], [3.0]) == []
+    assert spmv.rebalance_targets(cost, [0.0, 0.0, 0.0, 0.0]) == [1000, 2000, 3000]

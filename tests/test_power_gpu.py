@@ -113,22 +113,28 @@ def _free_port():
     return port
 
 
-def _rank_main(rank, world, port, exchange, out_dir):
+def _rank_main(rank, world, port, exchange, out_dir, rebalance=False):
     import torch.distributed as dist
     from spmv_samples_b200 import generate as gen
     from spmv_samples_b200.dist import PowerIteration, shard_rows
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    m = gen.rmat(14, 16, 7, offset=torch.int64)
+    m = gen.rmat(19 if rebalance else 14, 16, 7, offset=torch.int64)
     shard = shard_rows(m, rank, world)
     it = PowerIteration(shard, m.n_rows, kind="auto", exchange=exchange)
+    if rebalance:
+        # a deliberately lopsided split first, then two rounds of re-splitting from measured times
+        it.set_shard(shard_rows(m, rank, world, row_bounds=[0, m.n_rows // 64, m.n_rows]))
+        for _ in range(2):
+            it.step()
+            it.rebalance(m, steps=3)
     for _ in range(6):
         it.step()
     torch.cuda.synchronize()
     np.save(os.path.join(out_dir, f"x_{exchange}_{rank}.npy"), it.current_x().cpu().numpy())
     open(os.path.join(out_dir, f"ex_{exchange}_{rank}.txt"), "w").write(
-        it.exchange + " " + ",".join(map(str, shard.row_bounds)))
+        it.exchange + " " + ",".join(map(str, it.shard.row_bounds)))
     it.close()
     dist.destroy_process_group()
 
@@ -154,6 +160,54 @@ def test_two_gpu_sharded_iteration_matches_single_gpu(tmp_path, exchange):
     ref = it.current_x().cpu().numpy()
     it.close()
     assert np.linalg.norm(x0.astype(np.float64) - ref) <= 1e-5 * np.linalg.norm(ref)
+
+
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+def test_two_gpu_rebalanced_split_matches_single_gpu(tmp_path, exchange):
+    """Start from a lopsided split, re-split twice from measured per-rank kernel times: the
+    iteration must still be the single-GPU one, and the split must have moved towards balance."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    from spmv_samples_b200 import generate as gen
+    from spmv_samples_b200.dist import PowerIteration, shard_rows
+    mp.spawn(_rank_main, args=(2, _free_port(), exchange, str(tmp_path), True), nprocs=2, join=True)
+    x0 = np.load(tmp_path / f"x_{exchange}_0.npy")
+    x1 = np.load(tmp_path / f"x_{exchange}_1.npy")
+    assert np.array_equal(x0, x1)
+    b0 = open(tmp_path / f"ex_{exchange}_0.txt").read().split(" ")[1]
+    b1 = open(tmp_path / f"ex_{exchange}_1.txt").read().split(" ")[1]
+    assert b0 == b1                                     # every rank derived the same split
+    m = gen.rmat(19, 16, 7, offset=torch.int64)         # big enough for kernel times to differ
+    mid = int(b0.split(",")[1])
+    assert m.n_rows // 64 < mid < m.n_rows              # the boundary moved off the lopsided start
+    it = PowerIteration(shard_rows(m, 0, 1), m.n_rows, kind="auto")
+    for _ in range(6):
+        it.step()
+    ref = it.current_x().cpu().numpy()
+    it.close()
+    assert np.linalg.norm(x0.astype(np.float64) - ref) <= 1e-5 * np.linalg.norm(ref)
+
+
+@pytest.mark.parametrize("weight", [(1, 1), (0, 1), (1, 4), (3, 1)])
+@pytest.mark.parametrize("off", [np.int32, np.int64])
+def test_rows_at_cost_matches_the_oracle(weight, off):
+    from spmv_samples_b200 import spmv
+    rng = np.random.default_rng(5)
+    for Ap in (g.rmat(12, 16, 3, offset_dtype=off)[0], g.ragged(3000, 3000, 9.0, 4, offset_dtype=off)[0],
+               np.zeros(1, dtype=off), np.zeros(17, dtype=off)):
+        n_rows, nnz = Ap.shape[0] - 1, int(Ap[-1])
+        total = weight[1] * nnz + weight[0] * n_rows
+        targets = sorted(set([0, total, total + 5] + spmv.split_targets(total, 7)
+                             + [int(v) for v in rng.integers(0, total + 1, 20)]))
+        got = spmv.rows_at_cost(dev(Ap), targets, weight)
+        assert got == cpu.rows_at_cost(Ap, targets, weight).tolist()
+        if n_rows:
+            for parts in (2, 3, 8):
+                expect = [0] + cpu.rows_at_cost(Ap, spmv.split_targets(total, parts), weight).tolist() + [n_rows]
+                assert spmv.row_split(dev(Ap), parts, weight=weight) == expect
+                if weight == (1, 1):
+                    assert expect == cpu.row_split(Ap, parts).tolist()   # the merge path itself
 
 
 @pytest.mark.parametrize("slots", [1, 2, 3, 4])
