@@ -468,3 +468,46 @@ def test_semiring_needs_the_merge_kernel():
     assert ei.value.status == 4
     with pytest.raises(_lib.SpmvB200Error):
         spmv.spmv_ex("merge", *d, y, semiring="min_plus", alpha_dev=torch.ones(1, device="cuda"))
+
+
+# ------------------------------------------------------------------ poisoned surroundings
+def _embed(a, poison, pad=64):
+    """a copied into the middle of a larger device buffer whose other elements are `poison`;
+    returns (view of the middle, whole buffer).  pad elements = a multiple of 16 bytes."""
+    buf = torch.full((pad + a.shape[0] + pad,), poison, dtype=torch.from_numpy(a[:0].copy()).dtype, device="cuda")
+    buf[pad:pad + a.shape[0]] = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return buf[pad:pad + a.shape[0]], buf
+
+
+@pytest.mark.parametrize("kind", OURS)
+@pytest.mark.parametrize("case", ["nnz_not_multiple_of_4", "single_row_single_nnz", "o64_mixed",
+                                  "long_rows_f64", "one_huge_row_between_empties",
+                                  "all_nnz_in_last_row", "exact_tile_multiple", "n_cols_1"])
+def test_neighbouring_memory_is_neither_used_nor_written(case, kind):
+    """No sanitizer on this pool, so the arrays sit inside poisoned buffers: column indices next
+    to Aj point into NaN padding around x, values next to Ax are NaN, offsets next to Ap are out
+    of range, and y is fenced by sentinels.  The kernels read whole aligned 16-byte vectors and
+    mask; a masked element that leaked into a result, or a store outside y, shows up here."""
+    from spmv_samples_b200 import spmv
+    Ap, Aj, Ax = EDGE[case]()
+    n_rows, nnz = Ap.shape[0] - 1, int(Ap[-1])
+    n_cols = {"n_cols_1": 1}.get(case, int(Aj.max()) + 1 if Aj.size else 10)
+    x = g.gen_x(23, n_cols, Ax.dtype)
+    dAp, _k1 = _embed(Ap, nnz + 17)
+    dAj, _k2 = _embed(Aj, n_cols + 5)          # lands in the NaN padding behind x
+    dAx, _k3 = _embed(Ax, float("nan"))
+    dx, _k4 = _embed(x, float("nan"))
+    dy, ybuf = _embed(np.zeros(n_rows, dtype=Ax.dtype), 12345.0)
+    dy.fill_(float("nan"))                      # every element must be overwritten
+    spmv.SpMV(kind, n_rows, n_cols, nnz, dAp, dAj, dAx, dx, dy)
+    torch.cuda.synchronize()
+    assert_within_tolerance(dy.cpu().numpy(), Ap, Aj, Ax, x, f"poisoned {case}/{kind}")
+    fence = torch.cat([ybuf[:64], ybuf[64 + n_rows:]])
+    assert bool((fence == 12345.0).all()), "a store landed outside y"
+    # the generalised (semiring) kernel and SpMM read the same way
+    if kind == "merge":
+        dy.fill_(float("nan"))
+        spmv.spmv_ex("merge", dAp, dAj, dAx, dx, dy, semiring="min_plus")
+        torch.cuda.synchronize()
+        assert np.array_equal(dy.cpu().numpy(), cpu.spmv_semiring(Ap, Aj, Ax, x, "min_plus"))
+        assert bool((torch.cat([ybuf[:64], ybuf[64 + n_rows:]]) == 12345.0).all())
