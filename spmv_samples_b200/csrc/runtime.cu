@@ -43,6 +43,8 @@ std::map<std::string, int64_t> &options() {
         {"merge_carveout", -1},  // shared-memory carveout (percent) of the merge tile kernel
         {"l2_fetch_granularity", 0},  // 32/64/128: cudaLimitMaxL2FetchGranularity; 0 = leave
         {"spmm_force_vector", 0},     // 1: SpMM always takes the row-per-sub-warp kernel
+        {"spmm_by_columns", 0},       // 1: merge-class SpMM as K merge-path SpMVs (ablation)
+        {"spmm_force_merge", 0},      // 1: SpMM always takes the merge-path tile kernel
         {"merge_staging", 0},    // 0: Aj/Ax into registers (default); 1: TMA bulk copies to smem
         {"auto_kind", -1},       // -1: selector decides; else force a SPMVB200_KIND_*
         {"cusparse_preprocess", 0},  // 1: run cusparseSpMV_preprocess when a plan is built.  Only

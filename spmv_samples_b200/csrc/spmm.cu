@@ -207,6 +207,252 @@ int launch_K(int width, int32_t n_rows, OffT nnz, const OffT *Ap, const int32_t 
 #undef GO
 }
 
+// ------------------------------------------------------------ merge-path tile kernel, K-wide
+// The tile algorithm of merge.cu (register-staged nonzeros, byte flags at row starts, segmented
+// scan, one thread per row end) with a K-vector per nonzero: one gather fetches the K values of
+// X's row, the scan runs K times over values that share one set of flags.  Balances hub rows
+// exactly like the SpMV kernel and keeps the K-fold amortisation of the gather.
+constexpr int kMsBlock = 128;
+// items per thread: 8 for two floats per nonzero, else 4.  The scan's shuffles and barriers are
+// paid per thread and the gathers per item, so more items per thread pay until the K-vectors
+// cost occupancy: R-MAT scale 24, fp32, 4 -> 8 items: K = 2 1590 -> 1422 us (40 registers),
+// K = 4 2111 -> 2281 us (40 -> 64 registers).
+template <int K, typename ValT> constexpr int ms_ipt() { return K * (int)sizeof(ValT) <= 8 ? 8 : 4; }
+template <int K, typename ValT> constexpr int ms_tile() { return kMsBlock * ms_ipt<K, ValT>() - 4; }
+
+template <int K, typename OffT, typename ValT>
+__global__ void __launch_bounds__(kMsBlock)
+merge_spmm_tile_kernel(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap, const int32_t *__restrict__ Aj,
+                       const ValT *__restrict__ Ax, const ValT *__restrict__ X, int64_t ldx,
+                       ValT *__restrict__ Y, int64_t ldy, const ValT *__restrict__ alpha_dev,
+                       const int32_t *__restrict__ coords_x, int32_t *__restrict__ carry_row,
+                       ValT *__restrict__ carry_val) {
+    constexpr int IPT = ms_ipt<K, ValT>();
+    constexpr int kMsSlots = kMsBlock * IPT;
+    constexpr int kMsTile = kMsSlots - 4;  // path items per tile (slot 0 sits on a 16-byte boundary)
+    __shared__ __align__(16) ValT s_scan[kMsSlots * K];
+    __shared__ __align__(16) unsigned char s_flag[kMsSlots];
+    __shared__ ValT s_wval[kMsBlock / 32][K];
+    __shared__ int s_wflag[kMsBlock / 32];
+
+    const int tid = threadIdx.x;
+    const int64_t tile = blockIdx.x;
+    const int64_t total = (int64_t)n_rows + (int64_t)nnz;
+    const int64_t d0 = tile * kMsTile;
+    const int64_t d1 = d0 + kMsTile < total ? d0 + kMsTile : total;
+    const int32_t sx = __ldg(coords_x + tile);
+    const int32_t ex = __ldg(coords_x + tile + 1);
+    const int64_t sy = d0 - sx;
+    const int R = ex - sx;                // rows that end inside this tile
+    const int Z = (int)((d1 - ex) - sy);  // nonzeros inside this tile
+    const int shift = (int)(sy & 3);      // slot s holds tile-local nonzero s - shift
+    const int64_t a0 = sy - shift;
+
+#pragma unroll
+    for (int i = 0; i < IPT; i += 4) *reinterpret_cast<uint32_t *>(s_flag + tid * IPT + i) = 0u;
+    const int slot0 = tid * IPT;
+    const uint64_t pol_stream = policy_evict_first();
+    int c[IPT];
+    ValT a[IPT];
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+        c[i] = 0;
+        a[i] = (ValT)0;
+    }
+    if (slot0 < shift + Z) {
+        const int64_t g = a0 + slot0;
+        if (g + IPT <= (int64_t)nnz) {
+#pragma unroll
+            for (int i = 0; i < IPT; i += 4) {
+                const int4 cv = ldg_stream_int4(Aj + g + i, pol_stream);
+                const typename Val4<ValT>::type av = ldg_stream_val4(Ax + g + i, pol_stream);
+                c[i] = cv.x; c[i + 1] = cv.y; c[i + 2] = cv.z; c[i + 3] = cv.w;
+                a[i] = av.x; a[i + 1] = av.y; a[i + 2] = av.z; a[i + 3] = av.w;
+            }
+        } else {  // the last vector of the matrix: element-wise, inside the arrays
+#pragma unroll
+            for (int i = 0; i < IPT; ++i) {
+                if (g + i < (int64_t)nnz) {
+                    c[i] = __ldg(Aj + g + i);
+                    a[i] = __ldg(Ax + g + i);
+                }
+            }
+        }
+    }
+    const ValT alpha = alpha_dev ? __ldg(alpha_dev) : (ValT)1;
+    __syncthreads();  // flags are clear
+
+    for (int j = tid; j < R; j += kMsBlock) {
+        const int64_t q = (int64_t)__ldg(Ap + sx + 1 + j) - sy;
+        if (q < Z) s_flag[(int)q + shift] = 1;
+    }
+    // ---- the K-wide gathers, all issued before the first use
+    ValT p[IPT][K];
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+        const int t = slot0 + i - shift;
+        if (t >= 0 && t < Z) {
+            load_row<K>(X + (int64_t)c[i] * ldx, p[i]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; ++k) p[i][k] = (ValT)0;
+            a[i] = (ValT)0;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < IPT; ++i)
+#pragma unroll
+        for (int k = 0; k < K; ++k) p[i][k] *= a[i];
+    __syncthreads();  // flags are set
+
+    // ---- segmented scan: one set of flags, K values
+    unsigned long long fbits = 0ull;
+#pragma unroll
+    for (int i = 0; i < IPT; i += 4)
+        fbits |= (unsigned long long)*reinterpret_cast<const uint32_t *>(s_flag + slot0 + i) << (8 * i);
+    int flag = fbits != 0ull;
+    ValT val[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        ValT v = (ValT)0;
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) v = ((fbits >> (8 * i)) & 1ull) ? p[i][k] : v + p[i][k];
+        val[k] = v;
+    }
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int pf = __shfl_up_sync(0xffffffffu, flag, d);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const ValT pv = __shfl_up_sync(0xffffffffu, val[k], d);
+            if (lane >= d && !flag) val[k] += pv;
+        }
+        if (lane >= d) flag |= pf;
+    }
+    if (lane == 31) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) s_wval[warp][k] = val[k];
+        s_wflag[warp] = flag;
+    }
+    int ef = __shfl_up_sync(0xffffffffu, flag, 1);
+    ValT run[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        run[k] = __shfl_up_sync(0xffffffffu, val[k], 1);
+        if (lane == 0) run[k] = (ValT)0;
+    }
+    if (lane == 0) ef = 0;
+    __syncthreads();
+    if (!ef) {  // nothing in this warp before the thread starts a row: the earlier warps carry in
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            ValT wv = (ValT)0;
+#pragma unroll
+            for (int w = 0; w < kMsBlock / 32; ++w) {
+                if (w < warp) {
+                    const ValT v = s_wval[w][k];
+                    wv = s_wflag[w] ? v : wv + v;
+                }
+            }
+            run[k] += wv;
+        }
+    }
+    // K planes of kMsSlots values: a thread's four consecutive slots of one plane are one
+    // 16-byte (fp32) store at a 16-byte lane stride -- conflict-free, where a [slot][K] layout
+    // put the lanes 64 bytes apart (4-way conflicts on the pipe the gathers also need)
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        ValT r = run[k];
+        ValT out4[IPT];
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            r = ((fbits >> (8 * i)) & 1ull) ? p[i][k] : r + p[i][k];
+            out4[i] = r;
+        }
+#pragma unroll
+        for (int i = 0; i < IPT; i += 4)
+            store_row<4>(s_scan + k * kMsSlots + slot0 + i, reinterpret_cast<const ValT(&)[4]>(out4[i]));
+    }
+    __syncthreads();
+
+    // ---- one thread per row end; row sx+j covers tile-local nonzeros [max(Ap[sx+j]-sy,0), Ap[sx+j+1]-sy)
+    for (int j = tid; j < R; j += kMsBlock) {
+        const int64_t b64 = (int64_t)__ldg(Ap + sx + j) - sy;
+        const int q = (int)((int64_t)__ldg(Ap + sx + 1 + j) - sy);
+        const int b = b64 > 0 ? (int)b64 : 0;
+        ValT out[K];
+        if (q > b) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) out[k] = alpha * s_scan[k * kMsSlots + q - 1 + shift];
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; ++k) out[k] = (ValT)0;
+        }
+        store_row<K>(Y + ((int64_t)sx + j) * ldy, out);
+    }
+    if (tid == 0) {
+        const int64_t lq = R > 0 ? (int64_t)__ldg(Ap + ex) - sy : 0;
+        const int lastq = lq > 0 ? (int)lq : 0;
+        carry_row[tile] = ex;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            carry_val[tile * K + k] = Z > lastq ? s_scan[k * kMsSlots + Z - 1 + shift] : (ValT)0;
+    }
+}
+
+// One thread per tile: the head of a run of tiles whose carry lands in one row adds the run's
+// carries to that row of Y, in tile order (deterministic).
+template <int K, typename ValT>
+__global__ void __launch_bounds__(256)
+merge_spmm_fixup_kernel(int32_t n_rows, int64_t num_tiles, const int32_t *__restrict__ carry_row,
+                        const ValT *__restrict__ carry_val, ValT *__restrict__ Y, int64_t ldy,
+                        const ValT *__restrict__ alpha_dev) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_tiles) return;
+    const int32_t row = carry_row[t];
+    if (row >= n_rows) return;
+    if (t > 0 && carry_row[t - 1] == row) return;
+    ValT sum[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) sum[k] = carry_val[t * K + k];
+    for (int64_t u = t + 1; u < num_tiles && carry_row[u] == row; ++u)
+#pragma unroll
+        for (int k = 0; k < K; ++k) sum[k] += carry_val[u * K + k];
+    const ValT alpha = alpha_dev ? __ldg(alpha_dev) : (ValT)1;
+    ValT *y = Y + (int64_t)row * ldy;
+#pragma unroll
+    for (int k = 0; k < K; ++k) y[k] += alpha * sum[k];
+}
+
+template <int K, typename OffT, typename ValT>
+int launch_spmm_merge_K(int32_t n_rows, OffT nnz, const OffT *Ap, const int32_t *Aj, const ValT *Ax,
+                        const ValT *X, int64_t ldx, ValT *Y, int64_t ldy, const ValT *alpha_dev,
+                        cudaStream_t stream) {
+    const int64_t total = (int64_t)n_rows + (int64_t)nnz;
+    constexpr int kMsTile = ms_tile<K, ValT>();
+    const int64_t num_tiles = (total + kMsTile - 1) / kMsTile;
+    if (num_tiles > 0x7fffffffLL) return SPMVB200_ERR_UNSUPPORTED;
+    void *coords = nullptr, *crow = nullptr, *cval = nullptr;
+    SPMV_TRY(scratch_get(stream, SCRATCH_COORDS, (size_t)(num_tiles + 1) * sizeof(int32_t), &coords));
+    SPMV_TRY(scratch_get(stream, SCRATCH_CARRY_ROW, (size_t)num_tiles * sizeof(int32_t), &crow));
+    SPMV_TRY(scratch_get(stream, SCRATCH_CARRY_VAL, (size_t)num_tiles * K * sizeof(ValT), &cval));
+    SPMV_TRY(launch_partition<OffT>(n_rows, nnz, Ap, kMsTile, num_tiles + 1, static_cast<int32_t *>(coords),
+                                    stream));
+    {
+        KernelTimerScope timed(stream);
+        merge_spmm_tile_kernel<K, OffT, ValT><<<(unsigned)num_tiles, kMsBlock, 0, stream>>>(
+            n_rows, nnz, Ap, Aj, Ax, X, ldx, Y, ldy, alpha_dev, static_cast<const int32_t *>(coords),
+            static_cast<int32_t *>(crow), static_cast<ValT *>(cval));
+    }
+    SPMV_LAUNCH_CHECK();
+    merge_spmm_fixup_kernel<K, ValT><<<(unsigned)((num_tiles + 255) / 256), 256, 0, stream>>>(
+        n_rows, num_tiles, static_cast<const int32_t *>(crow), static_cast<const ValT *>(cval), Y, ldy,
+        alpha_dev);
+    SPMV_LAUNCH_CHECK();
+    return SPMVB200_OK;
+}
+
 // row-major [n x k] (leading dimension ld) <-> k contiguous vectors of length n
 template <typename ValT>
 __global__ void __launch_bounds__(256)
@@ -278,9 +524,17 @@ int launch_spmm(int k, int32_t n_rows, int32_t n_cols, OffT nnz, const OffT *Ap,
     if (k != 2 && k != 4 && k != 8) return SPMVB200_ERR_UNSUPPORTED;
     spmvb200_row_stats_t st;
     SPMV_TRY(row_stats<OffT>(n_rows, (int64_t)nnz, Ap, &st, stream, true));
-    if (st.chosen_kind == SPMVB200_KIND_MERGE && option_get("spmm_force_vector", 0) == 0)
-        return launch_spmm_by_columns<OffT, ValT>(k, n_rows, n_cols, nnz, Ap, Aj, Ax, X, ldx, Y, ldy,
-                                                  alpha_dev, stream);
+    const bool force_merge = option_get("spmm_force_merge", 0) > 0;
+    if (force_merge || (st.chosen_kind == SPMVB200_KIND_MERGE && option_get("spmm_force_vector", 0) == 0)) {
+        if (!force_merge && option_get("spmm_by_columns", 0) > 0)  // ablation: K merge-path SpMVs
+            return launch_spmm_by_columns<OffT, ValT>(k, n_rows, n_cols, nnz, Ap, Aj, Ax, X, ldx, Y, ldy,
+                                                      alpha_dev, stream);
+        switch (k) {
+            case 2: return launch_spmm_merge_K<2, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, X, ldx, Y, ldy, alpha_dev, stream);
+            case 4: return launch_spmm_merge_K<4, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, X, ldx, Y, ldy, alpha_dev, stream);
+            default: return launch_spmm_merge_K<8, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, X, ldx, Y, ldy, alpha_dev, stream);
+        }
+    }
     int width = (int)option_get("vector_width", 0);
     if (width <= 0) width = pick_width_from_mean((double)nnz / (double)n_rows);
     switch (k) {

@@ -45,24 +45,85 @@ def check(Y, Ap, Aj, Ax, X, alpha=1.0):
         assert bad.size == 0, (j, bad[:5], err[bad[:5]], tol * scale[bad[:5]])
 
 
-@pytest.mark.parametrize("force_vector", [0, 1])
+ROUTES = {"auto": {}, "vector": {"spmm_force_vector": 1}, "merge": {"spmm_force_merge": 1},
+          "columns": {"spmm_by_columns": 1}}
+
+
+def run_route(route, fn):
+    from spmv_samples_b200 import spmv
+    for name, v in ROUTES[route].items():
+        spmv.set_option(name, v)
+    try:
+        fn()
+    finally:
+        for name in ROUTES[route]:
+            spmv.set_option(name, 0)
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("route", sorted(ROUTES))
 @pytest.mark.parametrize("k", [2, 4, 8])
 @pytest.mark.parametrize("family", sorted(FAMILIES))
-def test_spmm_matches_k_spmvs(family, k, force_vector):
-    """force_vector=0: the selector's route (power-law matrices go column by column through
-    merge-path); force_vector=1: the multi-vector row kernel on every matrix, hub rows included."""
+def test_spmm_matches_k_spmvs(family, k, route):
+    """auto: the selector's route (power-law matrices take the merge-path SpMM tile kernel, the
+    rest the row kernel); vector / merge: that kernel on every matrix, hub rows included;
+    columns: the ablation that runs K merge-path SpMVs on merge-class matrices."""
     from spmv_samples_b200 import spmv
     Ap, Aj, Ax = FAMILIES[family]()
     n_rows, n_cols = Ap.shape[0] - 1, int(Aj.max()) + 1
     X = make_X(n_cols, k, Ax.dtype)
     Y = torch.full((n_rows, k), float("nan"), dtype=dev(Ax).dtype, device="cuda")
-    spmv.set_option("spmm_force_vector", force_vector)
-    try:
-        spmv.spmm(dev(Ap), dev(Aj), dev(Ax), dev(X), Y)
-    finally:
-        spmv.set_option("spmm_force_vector", 0)
-    torch.cuda.synchronize()
+    run_route(route, lambda: spmv.spmm(dev(Ap), dev(Aj), dev(Ax), dev(X), Y))
     check(Y.cpu().numpy(), Ap, Aj, Ax, X)
+
+
+def _csr(lens, n_cols, seed=0, dtype=np.float32, off=np.int32):
+    rng = np.random.default_rng(seed)
+    Ap = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=Ap[1:])
+    nnz = int(Ap[-1])
+    return Ap.astype(off), rng.integers(0, n_cols, nnz).astype(np.int32), rng.uniform(-1, 1, nnz).astype(dtype)
+
+
+MERGE_EDGE = {
+    "all_rows_empty": lambda: _csr([0] * 777, 10),
+    "single_row_single_nnz": lambda: _csr([1], 5),
+    "single_row_100k": lambda: _csr([100003], 4096),
+    "hub_between_empties": lambda: _csr([0] * 100 + [50001] + [0] * 100, 999),
+    "all_nnz_in_last_row": lambda: _csr([0] * 5000 + [7777], 100),
+    "all_nnz_in_first_row": lambda: _csr([7777] + [0] * 5000, 100),
+    "nnz_not_multiple_of_4": lambda: _csr([3, 1, 2, 5, 0, 7, 1], 9),
+    "exact_tile_multiple": lambda: _csr([3] * 127, 64),            # 127 rows + 381 nnz = 508 path items
+    "tile_boundary_on_row_end": lambda: _csr([507, 507], 64),
+    "exact_tile_multiple_1020": lambda: _csr([9] * 102, 64),       # 102 rows + 918 nnz = 1020 (8 items/thread)
+    "tile_boundary_on_row_end_1020": lambda: _csr([1019, 1019, 3], 64),
+    "n_cols_1": lambda: _csr([1, 0, 1, 1, 0] * 50, 1),
+    "long_rows_f64": lambda: _csr([4099, 1, 4097, 0, 8191], 512, dtype=np.float64),
+    "o64_mixed": lambda: _csr([5, 0, 300, 2, 2, 9000, 1], 700, off=np.int64),
+}
+
+
+@pytest.mark.parametrize("k", [2, 4, 8])
+@pytest.mark.parametrize("case", sorted(MERGE_EDGE))
+def test_merge_spmm_edge_cases_strides_and_alpha(case, k):
+    """The merge-path SpMM tile kernel on the edge cases of the SpMV suite, with leading
+    dimensions larger than k, alpha, and sentinels around the k columns of Y."""
+    from spmv_samples_b200 import spmv
+    Ap, Aj, Ax = MERGE_EDGE[case]()
+    n_rows = Ap.shape[0] - 1
+    n_cols = {"n_cols_1": 1}.get(case, int(Aj.max()) + 1 if Aj.size else 10)
+    X = make_X(n_cols, k, Ax.dtype)
+    tdt = dev(Ax).dtype
+    Xd = torch.full((n_cols, 16), float("nan"), dtype=tdt, device="cuda")
+    Xd[:, :k] = dev(X)
+    Yd = torch.full((n_rows, 24), 777.0, dtype=tdt, device="cuda")
+    Yd[:, :k] = float("nan")
+    alpha = torch.tensor([1.5], dtype=tdt, device="cuda")
+    run_route("merge", lambda: spmv.spmm(dev(Ap), dev(Aj), dev(Ax), Xd[:, :k], Yd[:, :k], alpha_dev=alpha))
+    check(Yd[:, :k].cpu().numpy(), Ap, Aj, Ax, X, alpha=1.5)
+    assert bool((Yd[:, k:] == 777.0).all())              # nothing written outside the k columns
+    if case == "all_rows_empty":
+        assert bool((Yd[:, :k] == 0).all())
 
 
 @pytest.mark.parametrize("width", [1, 2, 8, 32])

@@ -6,7 +6,11 @@ from spmv_samples_b200 import generate as gen, spmv
 p = argparse.ArgumentParser()
 p.add_argument("--configs", default="c1,c2,c3,c4")
 p.add_argument("--iters", type=int, default=10)
+p.add_argument("--opts", default="", help="library options, name=value,... (e.g. spmm_by_columns=1)")
 a = p.parse_args()
+for kv in filter(None, a.opts.split(",")):
+    name, v = kv.split("=")
+    spmv.set_option(name, int(v))
 flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
 
 
