@@ -35,8 +35,30 @@ for r in range(a.parts):
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     ts.sort()
+    # how much of a call is the tile kernel, and what the norm pass costs on this shard
+    import ctypes
+    from spmv_samples_b200 import _lib
+    ms, cnt = ctypes.c_double(), ctypes.c_int64()
+    spmv.set_option("time_main_kernel", 1)
+    _lib.lib().spmvb200_main_kernel_time(ctypes.byref(ms), ctypes.byref(cnt))
+    for _ in range(5):
+        spmv.spmv_ex(a.kind, m.Ap, m.Aj, m.Ax, x, y, n_cols=gm.n_cols)
+    torch.cuda.synchronize()
+    _lib.lib().spmvb200_main_kernel_time(ctypes.byref(ms), ctypes.byref(cnt))
+    spmv.set_option("time_main_kernel", 0)
+    main_ms = ms.value / max(cnt.value, 1)
+    ss = torch.zeros(1, dtype=torch.float64, device="cuda")
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(5):
+        _lib.lib().spmvb200_sum_squares(32 if y.element_size() == 4 else 64, y.numel(), y.data_ptr(), ss.data_ptr(),
+                                        torch.cuda.current_stream().cuda_stream)
+    e1.record()
+    torch.cuda.synchronize()
+    sumsq_ms = e0.elapsed_time(e1) / 5
     lens = (m.Ap[1:] - m.Ap[:-1])
     print(f"  shard {r}: rows={m.n_rows:10d} nnz={m.nnz:11d} items={m.n_rows + m.nnz:11d} empty={int((lens == 0).sum()):10d} "
-          f"max_row={int(lens.max()):8d}  {ts[2]:8.3f} ms  {m.nnz / ts[2] / 1e6:7.1f} Gnnz/s", flush=True)
+          f"max_row={int(lens.max()):8d}  {ts[2]:8.3f} ms  {m.nnz / ts[2] / 1e6:7.1f} Gnnz/s   "
+          f"tile kernel {main_ms:7.3f} ms, partition+fixup {ts[2] - main_ms:6.3f} ms, sumsq {sumsq_ms:6.3f} ms", flush=True)
     del sh, m
     torch.cuda.empty_cache()
