@@ -384,27 +384,26 @@ def own_arm(args, rank, world, local_rank):
 
     # ---- e2e: the host-buffer API, x H2D + kernel + y D2H every step, pinned host memory
     e2e = None
-    if args.e2e_steps > 0:
+
+    def timed(fn):
+        barrier()
+        t0 = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t0
+        td = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        return float(td.item())
+
+    k, ns = args.e2e_steps, args.e2e_slots
+    if k > 0 and world == 1:
         mat = CsrMatrix.from_device(local)
-        ns = args.e2e_slots
         xs = [torch.empty(n_cols, dtype=local.Ax.dtype, pin_memory=True) for _ in range(ns)]
         ys = [torch.empty(local.n_rows, dtype=local.Ax.dtype, pin_memory=True) for _ in range(ns)]
         xs[0].copy_(it.current_x().cpu())
         for t in xs[1:]:
             t.copy_(xs[0])
         xn, yn = [t.numpy() for t in xs], [t.numpy() for t in ys]
-
-        def timed(fn):
-            barrier()
-            t0 = time.perf_counter()
-            fn()
-            dt = time.perf_counter() - t0
-            td = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            if world > 1:
-                dist.all_reduce(td, op=dist.ReduceOp.MAX)
-            return float(td.item())
-
-        k = args.e2e_steps
         for _ in range(2):
             mat.spmv(xn[0], yn[0], kind=args.kind)
         # one call at a time: upload, kernel, download, back to back
@@ -427,6 +426,28 @@ def own_arm(args, rank, world, local_rank):
                       f"{ns} steps in flight on {ns} streams.  serial_value: CsrMatrix.spmv, one step "
                       "at a time"}
         mat.close()
+    elif k > 0:
+        # row-sharded host-buffer call: every rank uploads its slice of x, the slices are
+        # all-gathered over NVLink, every rank downloads its slice of y
+        from spmv_samples_b200.dist import ShardedHostSpMV
+        hs = ShardedHostSpMV(shard, n, kind=args.kind, slots=ns)
+        rows_local = local.n_rows
+        xs = [torch.empty(rows_local, dtype=local.Ax.dtype, pin_memory=True) for _ in range(ns)]
+        ys = [torch.empty(rows_local, dtype=local.Ax.dtype, pin_memory=True) for _ in range(ns)]
+        xs[0].copy_(it.current_x()[shard.row_begin:shard.row_end].cpu())
+        for t in xs[1:]:
+            t.copy_(xs[0])
+        hs.spmv_many([xs[i % ns] for i in range(ns)], [ys[i % ns] for i in range(ns)])
+        dt = timed(lambda: hs.spmv_many([xs[i % ns] for i in range(k)], [ys[i % ns] for i in range(k)]))
+        e2e = {"value": 2.0 * nnz_total * k / dt / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": int(n_cols * xs[0].element_size()),
+               "d2h_bytes_per_step": int(n * ys[0].element_size()),
+               "steps": k, "ms_per_step": dt / k * 1e3,
+               "api": "spmv_samples_b200.dist.ShardedHostSpMV.spmv_many: matrix resident and "
+                      "row-sharded; every step each rank uploads its slice of x from pinned host "
+                      "memory, the slices are all-gathered over NVLink (NCCL), the SpMV runs, each rank "
+                      f"downloads its slice of y; bytes are totals over the ranks; {ns} steps in flight"}
+        hs.close()
 
     it.close()
     if rank == 0:

@@ -345,6 +345,74 @@ class PowerIteration:
             r.free()
 
 
+class ShardedHostSpMV:
+    """y = A x with x and y in HOST memory and everything sharded by rows: rank q holds the row
+    block of A, the slice x[row_begin:row_end] and the slice y[row_begin:row_end] (A square).
+    A call uploads the local slice of x, all-gathers the slices over NVLink (NCCL, uneven
+    slices) into a full-length device x, runs the SpMV and downloads the local slice of y -- so
+    the host link carries n values per call in total, not n per GPU.  `slots` calls are in flight
+    at once (own stream and device buffers each), like matrix.CsrMatrix.spmv_many on one GPU.
+    All ranks must submit in the same order (the all-gathers pair up by issue order)."""
+
+    def __init__(self, shard: Shard, n_global: int, kind: str = "auto", slots: int = 3, group=None):
+        import torch.distributed as dist
+        if not torch.cuda.is_available():
+            raise RuntimeError("ShardedHostSpMV needs a CUDA device; there is no CPU path")
+        if shard.csr.n_cols != n_global:
+            raise ValueError("the shard must carry the global column count")
+        self.dist, self.group = dist, group
+        self.shard, self.n, self.kind = shard, int(n_global), kind
+        self.world, self.rank = shard.world, shard.rank
+        dt = shard.csr.Ax.dtype
+        self._slots = []
+        for _ in range(int(slots)):
+            x = torch.empty(self.n, dtype=dt, device="cuda")
+            self._slots.append({
+                "stream": torch.cuda.Stream(), "x": x,
+                "y": torch.empty(shard.csr.n_rows, dtype=dt, device="cuda"),
+                "views": [x[shard.row_bounds[q]:shard.row_bounds[q + 1]] for q in range(self.world)]})
+        torch.cuda.synchronize()
+
+    @property
+    def n_slots(self) -> int:
+        return len(self._slots)
+
+    def submit(self, slot: int, x_local: torch.Tensor, y_local: torch.Tensor) -> None:
+        """x_local / y_local: this rank's slices, CPU tensors (pinned for the copies to overlap);
+        untouched until wait(slot)."""
+        sh, m, sl = self.shard, self.shard.csr, self._slots[slot]
+        rows = sh.row_end - sh.row_begin
+        if x_local.numel() != rows or y_local.numel() != rows or x_local.dtype != m.Ax.dtype \
+                or y_local.dtype != m.Ax.dtype or x_local.is_cuda or y_local.is_cuda:
+            raise ValueError("x_local / y_local must be CPU tensors of this rank's rows and the matrix dtype")
+        with torch.cuda.stream(sl["stream"]):
+            mine = sl["views"][self.rank]
+            mine.copy_(x_local, non_blocking=True)
+            if self.world > 1:
+                self.dist.all_gather(sl["views"], mine, group=self.group)
+            spmv_mod.spmv_ex(self.kind, m.Ap, m.Aj, m.Ax, sl["x"], sl["y"], n_cols=self.n,
+                             stream=sl["stream"])
+            y_local.copy_(sl["y"], non_blocking=True)
+
+    def wait(self, slot: int) -> None:
+        self._slots[slot]["stream"].synchronize()
+
+    def spmv_many(self, xs, ys) -> None:
+        """ys[i] = (A @ x_i)[local rows] for a sequence of right-hand sides given by local slices."""
+        k, n = self.n_slots, 0
+        for i, (x, y) in enumerate(zip(xs, ys)):
+            if i >= k:
+                self.wait(i % k)
+            self.submit(i % k, x, y)
+            n = i + 1
+        for s in range(min(n, k)):
+            self.wait(s)
+
+    def close(self):
+        torch.cuda.synchronize()
+        self._slots = []
+
+
 def init_distributed():
     """(rank, world, local_rank) from torchrun's environment; NCCL over NVLink when world > 1."""
     import torch.distributed as dist

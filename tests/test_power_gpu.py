@@ -189,6 +189,64 @@ def test_two_gpu_rebalanced_split_matches_single_gpu(tmp_path, exchange):
     assert np.linalg.norm(x0.astype(np.float64) - ref) <= 1e-5 * np.linalg.norm(ref)
 
 
+def _host_rank_main(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from spmv_samples_b200 import generate as gen
+    from spmv_samples_b200.dist import ShardedHostSpMV, shard_rows
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    m = gen.rmat(14, 16, 7, offset=torch.int64)
+    shard = shard_rows(m, rank, world)
+    hs = ShardedHostSpMV(shard, m.n_rows, kind="auto", slots=3)
+    r0, r1 = shard.row_begin, shard.row_end
+    xs = [torch.from_numpy(g.gen_x(200 + i, m.n_cols)[r0:r1].copy()).pin_memory() for i in range(7)]
+    ys = [torch.full((r1 - r0,), float("nan")).pin_memory() for _ in range(7)]
+    hs.spmv_many(xs, ys)
+    hs.close()
+    np.save(os.path.join(out_dir, f"y_{rank}.npy"), np.stack([y.numpy() for y in ys]))
+    np.save(os.path.join(out_dir, f"rows_{rank}.npy"), np.array([r0, r1]))
+    dist.destroy_process_group()
+
+
+def test_two_gpu_sharded_host_buffer_spmv(tmp_path):
+    """x and y sharded by rows in host memory: upload of the local slice, all-gather on the
+    device, SpMV, download of the local slice, three calls in flight."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_host_rank_main, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    Ap, Aj, Ax = g.rmat(14, 16, 7, offset_dtype=np.int64)
+    n = Ap.shape[0] - 1
+    got = np.empty((7, n), dtype=np.float32)
+    seen = 0
+    for rank in range(2):
+        r0, r1 = np.load(tmp_path / f"rows_{rank}.npy")
+        got[:, r0:r1] = np.load(tmp_path / f"y_{rank}.npy")
+        seen += r1 - r0
+    assert seen == n
+    for i in range(7):
+        x = g.gen_x(200 + i, n)
+        assert np.all(np.abs(got[i] - cpu.spmv_fp64(Ap, Aj, Ax, x)) <= 1e-5 * cpu.abs_scale(Ap, Aj, Ax, x))
+
+
+def test_sharded_host_buffer_spmv_single_rank():
+    from spmv_samples_b200 import generate as gen
+    from spmv_samples_b200.dist import ShardedHostSpMV, shard_rows
+    m = gen.uniform_rows(30000, 30000, 16, 4)
+    Ap, Aj, Ax = g.uniform_rows(30000, 30000, 16, 4)
+    hs = ShardedHostSpMV(shard_rows(m, 0, 1), m.n_rows, slots=2)
+    xs = [torch.from_numpy(g.gen_x(300 + i, m.n_cols)).pin_memory() for i in range(5)]
+    ys = [torch.full((m.n_rows,), float("nan")).pin_memory() for _ in range(5)]
+    hs.spmv_many(xs, ys)
+    for x, y in zip(xs, ys):
+        assert np.all(np.abs(y.numpy() - cpu.spmv_fp64(Ap, Aj, Ax, x.numpy()))
+                      <= 1e-5 * cpu.abs_scale(Ap, Aj, Ax, x.numpy()))
+    with pytest.raises(ValueError):
+        hs.submit(0, xs[0][:-1], ys[0])
+    hs.close()
+
+
 @pytest.mark.parametrize("weight", [(1, 1), (0, 1), (1, 4), (3, 1)])
 @pytest.mark.parametrize("off", [np.int32, np.int64])
 def test_rows_at_cost_matches_the_oracle(weight, off):
