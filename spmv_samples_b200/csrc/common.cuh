@@ -51,6 +51,10 @@ struct DeviceInfo {
 };
 int current_device_info(const DeviceInfo **out);
 
+// cudaFuncAttributePreferredSharedMemoryCarveout for `kernel` on the current device, applied
+// once per (device, kernel, value).  percent < 0 = the driver's default.
+int apply_carveout(const void *kernel, int64_t percent);
+
 // Per-(device, stream) scratch that survives across calls, grown on demand.
 // Slots keep independent buffers so a kernel can hold several at once.
 enum ScratchSlot { SCRATCH_COORDS = 0, SCRATCH_CARRY_ROW, SCRATCH_CARRY_VAL, SCRATCH_COUNTER,

@@ -317,6 +317,9 @@ merge_tile_reg_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
     constexpr int SLOTS = BLOCK * IPT;
     constexpr int TILE = SLOTS - 4;  // path items per tile
     __shared__ __align__(16) ValT s_scan[SLOTS];
+    // row-start flags, one byte per slot.  (One BIT per slot, set with atomicOr, saves 1.8 KB per
+    // 256-thread CTA and fits one more CTA per SM inside the 64 KB carveout, but measured slower:
+    // R-MAT scale 24 1146 -> 1166 us, scale 27 14.70 -> 14.93 ms.)
     __shared__ __align__(16) unsigned char s_flag[SLOTS];
     __shared__ ValT s_wval[BLOCK / 32];
     __shared__ int s_wflag[BLOCK / 32];
@@ -786,7 +789,14 @@ int launch_merge(const SpmvProblem<OffT, ValT> &p) {
 
     // "merge_staging": 0 (default) = Aj/Ax into registers, 1 = TMA bulk copies into shared
     // memory (kept for the ablation that decided against it; see merge_tile_reg_body)
-    const int64_t carveout = option_get("merge_carveout", -1);
+    // shared-memory carveout in percent of 228 KB; -1 = the driver's choice, -2 (default) = 64 KB
+    // for fp32 and the driver's choice for fp64.  The driver picks 100 KB to fit every CTA the
+    // registers allow, but the L1 half of the array is what holds the gathers in flight: R-MAT
+    // scale 27 15.04 ms at 100 KB, 14.70 at 64 KB, 14.87 at 32 KB, 16.4 at 132 KB; scale 24
+    // 1187 / 1146 / 1289 us.  fp64 tiles are twice as large and lose too many CTAs at 64 KB
+    // (65536 x 2048 fp64: 728 -> 796 us).
+    int64_t carveout = option_get("merge_carveout", -2);
+    if (carveout == -2) carveout = sizeof(ValT) == 4 ? 28 : -1;
     LaunchCfg lc;
     if (tma) {
         static int64_t attr_carveout = -2;  // per instantiation: last carveout applied
@@ -814,12 +824,7 @@ int launch_merge(const SpmvProblem<OffT, ValT> &p) {
         auto kernel = has_peers ? merge_tile_reg_kernel<RB, true, OffT, ValT>      // 40 regs, no spill
                       : occ     ? merge_tile_reg_kernel_occ8<RB, false, OffT, ValT>
                                 : merge_tile_reg_kernel<RB, false, OffT, ValT>;
-        static int64_t attr_carveout = -2;
-        if (attr_carveout != carveout) {
-            SPMV_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                               carveout < 0 ? (int)cudaSharedmemCarveoutDefault : (int)carveout));
-            attr_carveout = carveout;
-        }
+        SPMV_TRY(apply_carveout(reinterpret_cast<const void *>(kernel), carveout));
         make_launch_cfg(lc, dim3((unsigned)num_tiles), dim3(RB), 0, p.stream, p.x,
                         (size_t)p.n_cols * sizeof(ValT));
         KernelTimerScope timed(p.stream);

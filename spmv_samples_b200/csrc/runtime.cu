@@ -40,11 +40,12 @@ std::map<std::string, int64_t> &options() {
         {"light_width", 0},      // same for the dynamic-row kernel
         {"light_rows_per_claim", 0},  // 0: automatic
         {"time_main_kernel", 0}, // 1: cudaEvent bracket around each call's dominant kernel
-        {"merge_carveout", -1},  // shared-memory carveout (percent) of the merge tile kernel
+        {"merge_carveout", -2},  // shared-memory carveout (percent) of the merge tile kernel; -1: driver's, -2: by type
         {"l2_fetch_granularity", 0},  // 32/64/128: cudaLimitMaxL2FetchGranularity; 0 = leave
         {"spmm_force_vector", 0},     // 1: SpMM always takes the row-per-sub-warp kernel
         {"spmm_by_columns", 0},       // 1: merge-class SpMM as K merge-path SpMVs (ablation)
         {"spmm_force_merge", 0},      // 1: SpMM always takes the merge-path tile kernel
+        {"spmm_carveout", -1},        // shared-memory carveout (percent) of the merge-path SpMM kernel
         {"merge_staging", 0},    // 0: Aj/Ax into registers (default); 1: TMA bulk copies to smem
         {"auto_kind", -1},       // -1: selector decides; else force a SPMVB200_KIND_*
         {"cusparse_preprocess", 0},  // 1: run cusparseSpMV_preprocess when a plan is built.  Only
@@ -163,6 +164,20 @@ void fold_pending_locked() {
     g_ev_pending.clear();
 }
 }  // namespace
+
+int apply_carveout(const void *kernel, int64_t percent) {
+    const DeviceInfo *di = nullptr;
+    SPMV_TRY(current_device_info(&di));
+    static std::map<std::pair<int, const void *>, int64_t> applied;
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto key = std::make_pair(di->device, kernel);
+    auto it = applied.find(key);
+    if (it != applied.end() && it->second == percent) return SPMVB200_OK;
+    SPMV_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       percent < 0 ? (int)cudaSharedmemCarveoutDefault : (int)percent));
+    applied[key] = percent;
+    return SPMVB200_OK;
+}
 
 KernelTimerScope::KernelTimerScope(cudaStream_t s) : stream_(s) {
     if (option_get("time_main_kernel", 0) <= 0) return;

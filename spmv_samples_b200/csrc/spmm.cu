@@ -439,6 +439,8 @@ int launch_spmm_merge_K(int32_t n_rows, OffT nnz, const OffT *Ap, const int32_t 
     SPMV_TRY(scratch_get(stream, SCRATCH_CARRY_VAL, (size_t)num_tiles * K * sizeof(ValT), &cval));
     SPMV_TRY(launch_partition<OffT>(n_rows, nnz, Ap, kMsTile, num_tiles + 1, static_cast<int32_t *>(coords),
                                     stream));
+    SPMV_TRY(apply_carveout(reinterpret_cast<const void *>(&merge_spmm_tile_kernel<K, OffT, ValT>),
+                            option_get("spmm_carveout", -1)));
     {
         KernelTimerScope timed(stream);
         merge_spmm_tile_kernel<K, OffT, ValT><<<(unsigned)num_tiles, kMsBlock, 0, stream>>>(
