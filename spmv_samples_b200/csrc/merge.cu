@@ -10,22 +10,25 @@
 // agent's per-thread path search + serial merge (about 45 scalar shared-memory operations per
 // thread) is shared-memory-issue bound here (first ncu capture: mio_throttle + short
 // scoreboard dominant, 75 thread instructions per path item, 16 % of the HBM roofline):
-//   * a tile is 2044 path items; its row offsets and its Aj / Ax segments are staged into
-//     shared memory with TMA 1-D bulk copies (cp.async.bulk -> UBLKCP) completing on one
-//     mbarrier, with an L2 evict-first policy;
-//   * every thread owns 8 consecutive staged nonzeros: 128-bit shared loads of Aj and Ax, x
-//     gathered with an L2 evict-last policy, products kept in registers;
+//   * a tile is 1020 path items (128 threads, int32 offsets) or 2044 (256 threads, int64);
+//   * every thread owns 8 consecutive nonzeros: 128-bit evict-first loads of Aj and Ax from a
+//     16-byte aligned position straight into registers, x gathered with an L2 evict-last
+//     policy, products kept in registers (merge_tile_reg_body, the default).  The first version
+//     staged the tile's Ap / Aj / Ax segments in shared memory with TMA 1-D bulk copies
+//     (merge_tile_tma_kernel, option merge_staging = 1, kept under test as the ablation): the
+//     27-35 KB per CTA it takes come out of the L1 that holds the x gathers in flight, and it
+//     is 1.1x (int32 offsets) to 2.9x (R-MAT scale 27) slower -- DESIGN.md section 3, point 2;
 //   * rows are delimited by a byte flag per nonzero, scattered one thread per row end; the
 //     reduction is a segmented scan (serial in the thread, shuffles across the warp, one
 //     shared-memory hop across warps) -- no per-thread merge-path search at all;
-//   * the scanned values go back to shared memory once, and one thread per row end picks its
+//   * the scanned values go to shared memory once, and one thread per row end picks its
 //     row's total, so y is written coalesced;
 //   * only the row coordinate of each tile boundary is stored (int32); the nonzero
 //     coordinate is diagonal - row, which keeps the scratch 64-bit safe for free;
 //   * the tile carry-out goes to a fixup kernel that is deterministic (run-head threads sum
 //     their run in tile order; no atomics, unlike agent_segment_fixup.cuh:257,269).
-// Within a tile the work is bounded by construction (rows + nonzeros <= 2044), which is the
-// load-balance guarantee of the merge path; the in-tile phases are regular on top of it.
+// Within a tile the work is bounded by construction (rows + nonzeros <= tile size), which is
+// the load-balance guarantee of the merge path; the in-tile phases are regular on top of it.
 #include <climits>
 
 #include "common.cuh"
@@ -741,9 +744,6 @@ template int launch_merge_genl<int32_t, double>(const SpmvProblem<int32_t, doubl
 template int launch_merge_genl<int64_t, float>(const SpmvProblem<int64_t, float> &, int, const float *);
 template int launch_merge_genl<int64_t, double>(const SpmvProblem<int64_t, double> &, int, const double *);
 
-namespace {
-}  // namespace
-
 template <typename OffT>
 int launch_partition(int32_t n_rows, OffT nnz, const OffT *Ap, int64_t tile_items, int64_t n_coords,
                      int32_t *coords_x, cudaStream_t stream) {
@@ -787,8 +787,6 @@ int launch_merge(const SpmvProblem<OffT, ValT> &p) {
     SPMV_TRY(launch_partition<OffT>(p.n_rows, p.nnz, p.Ap, tile_items, num_tiles + 1,
                                     static_cast<int32_t *>(coords), p.stream));
 
-    // "merge_staging": 0 (default) = Aj/Ax into registers, 1 = TMA bulk copies into shared
-    // memory (kept for the ablation that decided against it; see merge_tile_reg_body)
     // shared-memory carveout in percent of 228 KB; -1 = the driver's choice, -2 (default) = 64 KB
     // for fp32 and the driver's choice for fp64.  The driver picks 100 KB to fit every CTA the
     // registers allow, but the L1 half of the array is what holds the gathers in flight: R-MAT
@@ -798,8 +796,10 @@ int launch_merge(const SpmvProblem<OffT, ValT> &p) {
     int64_t carveout = option_get("merge_carveout", -2);
     if (carveout == -2) carveout = sizeof(ValT) == 4 ? 28 : -1;
     LaunchCfg lc;
+    // "merge_staging": 0 (default) = Aj/Ax into registers, 1 = TMA bulk copies into shared
+    // memory (kept for the ablation that decided against it; see merge_tile_reg_body)
     if (tma) {
-        static int64_t attr_carveout = -2;  // per instantiation: last carveout applied
+        static int64_t attr_carveout = -3;  // per instantiation: last carveout applied
         constexpr size_t smem = merge_smem_bytes<OffT, ValT>();
         if (attr_carveout != carveout) {
             SPMV_CUDA_TRY(cudaFuncSetAttribute(merge_tile_tma_kernel<OffT, ValT>,
