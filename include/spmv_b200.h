@@ -118,7 +118,13 @@ enum {
 };
 /* beta_dev: optional DEVICE pointer to one value-typed scalar: y = alpha*A*x + beta*y (plus-times
  * only; merge-path kernel; merge_based/agent_spmv_orig.cuh:425-433 HAS_BETA).  NULL means 0 and y
- * is not read.  Fields after `stream` default to plus-times / no beta when zero-initialised. */
+ * is not read.  Fields after `stream` default to plus-times / no beta when zero-initialised.
+ * flags: SPMVB200_FLAG_STATIC_PATTERN -- the caller vouches that Ap (same pointer, n_rows, nnz)
+ * still holds what it held at the previous call on this stream, so the merge-path kernel may
+ * reuse that call's tile coordinates instead of searching again (an iterative solver's matrix;
+ * the reference re-derives everything per call, merge_based/dispatch_spmv_orig.cuh:613-660).
+ * The first call on a matrix, or any call after Ap's contents changed, must not pass it. */
+#define SPMVB200_FLAG_STATIC_PATTERN 1
 typedef struct {
     int32_t kind;
     int32_t offset_bits;
@@ -136,7 +142,7 @@ typedef struct {
     void *const *y_peers;
     spmvb200_stream_t stream;
     int32_t semiring;
-    int32_t reserved;
+    int32_t flags;
     const void *beta_dev;
 } spmvb200_args_t;
 SPMVB200_API int spmvb200_spmv(const spmvb200_args_t *args);

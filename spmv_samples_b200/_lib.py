@@ -16,6 +16,7 @@ CSRC = os.path.join(_PKG, "csrc")
 
 OK = 0
 KIND_MERGE, KIND_VECTOR, KIND_LIGHT, KIND_AUTO, KIND_CUSPARSE = 0, 1, 2, 3, 4
+FLAG_STATIC_PATTERN = 1   # SPMVB200_FLAG_STATIC_PATTERN
 SEMIRINGS = {"plus_times": 0, "min_plus": 1, "max_plus": 2, "or_and": 3}
 MAX_PEERS = 8
 IPC_HANDLE_BYTES = 64
@@ -35,7 +36,7 @@ class Args(C.Structure):
         ("Ap", C.c_void_p), ("Aj", C.c_void_p), ("Ax", C.c_void_p), ("x", C.c_void_p),
         ("y", C.c_void_p), ("alpha_dev", C.c_void_p), ("y_peers", C.POINTER(C.c_void_p)),
         ("stream", C.c_void_p),
-        ("semiring", C.c_int32), ("reserved", C.c_int32), ("beta_dev", C.c_void_p),
+        ("semiring", C.c_int32), ("flags", C.c_int32), ("beta_dev", C.c_void_p),
     ]
 
 

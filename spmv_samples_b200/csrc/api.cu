@@ -32,7 +32,7 @@ template <typename OffT, typename ValT>
 int run(int kind, int64_t n_rows, int64_t n_cols, int64_t nnz, const void *Ap, const int32_t *Aj,
         const void *Ax, const void *x, void *y, const void *alpha_dev, void *const *y_peers,
         int n_peers, cudaStream_t stream, int semiring = SPMVB200_SEMIRING_PLUS_TIMES,
-        const void *beta_dev = nullptr) {
+        const void *beta_dev = nullptr, int flags = 0) {
     if (n_rows < 0 || n_cols < 0 || nnz < 0) return SPMVB200_ERR_INVALID;
     if (n_rows > 0x7fffffffLL || n_cols > 0x7fffffffLL) return SPMVB200_ERR_INVALID;
     if (sizeof(OffT) == 4 && nnz > 0x7fffffffLL) return SPMVB200_ERR_INVALID;
@@ -58,6 +58,7 @@ int run(int kind, int64_t n_rows, int64_t n_cols, int64_t nnz, const void *Ap, c
     p.peers.n = n_peers;
     for (int i = 0; i < kMaxPeers; ++i) p.peers.ptr[i] = i < (n_peers < 0 ? 1 : n_peers) ? y_peers[i] : nullptr;
     p.stream = stream;
+    p.reuse_partition = (flags & SPMVB200_FLAG_STATIC_PATTERN) != 0;
 
     if (semiring != SPMVB200_SEMIRING_PLUS_TIMES || beta_dev) {
         // the generalised form lives in the merge-path kernel only (as in the reference)
@@ -76,10 +77,11 @@ int run(int kind, int64_t n_rows, int64_t n_cols, int64_t nnz, const void *Ap, c
 
 int run_untyped(const spmvb200_args_t *a) {
     if (!a) return SPMVB200_ERR_INVALID;
+    if (a->flags & ~SPMVB200_FLAG_STATIC_PATTERN) return SPMVB200_ERR_INVALID;
     cudaStream_t s = static_cast<cudaStream_t>(a->stream);
 #define GO(O, V)                                                                              \
     return run<O, V>(a->kind, a->n_rows, a->n_cols, a->nnz, a->Ap, a->Aj, a->Ax, a->x, a->y,  \
-                     a->alpha_dev, a->y_peers, a->n_peers, s, a->semiring, a->beta_dev)
+                     a->alpha_dev, a->y_peers, a->n_peers, s, a->semiring, a->beta_dev, a->flags)
     if (a->offset_bits == 32 && a->value_bits == 32) GO(int32_t, float);
     if (a->offset_bits == 32 && a->value_bits == 64) GO(int32_t, double);
     if (a->offset_bits == 64 && a->value_bits == 32) GO(int64_t, float);

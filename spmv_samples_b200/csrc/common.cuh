@@ -60,6 +60,19 @@ int apply_carveout(const void *kernel, int64_t percent);
 enum ScratchSlot { SCRATCH_COORDS = 0, SCRATCH_CARRY_ROW, SCRATCH_CARRY_VAL, SCRATCH_COUNTER,
                    SCRATCH_STATS, SCRATCH_MISC, SCRATCH_SPMM_X, SCRATCH_SPMM_Y, SCRATCH_NUM_SLOTS };
 int scratch_get(cudaStream_t stream, ScratchSlot slot, size_t bytes, void **out);
+
+// What the last merge-path partition launched on a (device, stream) wrote, and where: lets a
+// caller that vouches for an unchanged matrix (SPMVB200_FLAG_STATIC_PATTERN) skip the search.
+struct PartitionTag {
+    const void *coords, *Ap;
+    int64_t n_rows, nnz, tile_items, n_coords;
+    bool operator==(const PartitionTag &o) const {
+        return coords == o.coords && Ap == o.Ap && n_rows == o.n_rows && nnz == o.nnz &&
+               tile_items == o.tile_items && n_coords == o.n_coords;
+    }
+};
+bool partition_tag_matches(cudaStream_t stream, const PartitionTag &tag);
+void partition_tag_store(cudaStream_t stream, const PartitionTag &tag);
 void scratch_release_all();
 
 int64_t option_get(const char *name, int64_t fallback);
@@ -99,6 +112,7 @@ struct SpmvProblem {
     const ValT *alpha_dev;  // device scalar or nullptr (= 1)
     PeerOut peers;
     cudaStream_t stream;
+    bool reuse_partition = false;  // SPMVB200_FLAG_STATIC_PATTERN: tile coordinates may be reused
 };
 
 // launchers (one translation unit each)
@@ -111,7 +125,7 @@ template <typename OffT, typename ValT> int launch_cusparse(const SpmvProblem<Of
 template <typename OffT, typename ValT> int launch_auto(const SpmvProblem<OffT, ValT> &p);
 template <typename OffT>
 int launch_partition(int32_t n_rows, OffT nnz, const OffT *Ap, int64_t tile_items, int64_t n_coords,
-                     int32_t *coords_x, cudaStream_t stream);
+                     int32_t *coords_x, cudaStream_t stream, bool reuse = false);
 template <typename OffT>
 int row_stats(int64_t n_rows, int64_t nnz, const OffT *Ap, spmvb200_row_stats_t *out,
               cudaStream_t stream, bool use_cache);

@@ -496,7 +496,25 @@ merge_fixup_kernel(int32_t n_rows, int64_t num_tiles, const int32_t *__restrict_
     if (row >= n_rows) return;
     if (t > 0 && carry_row[t - 1] == row) return;
     ValT sum = carry_val[t];
-    for (int64_t u = t + 1; u < num_tiles && carry_row[u] == row; ++u) sum += carry_val[u];
+    // a hub row spans hundreds of tiles: walk its run eight tiles at a time so that the loads
+    // of a batch are in flight together (one load per trip made this kernel as long as the
+    // search: 73 us on R-MAT scale 27); the additions stay in tile order
+    bool more = true;
+    for (int64_t u = t + 1; more && u < num_tiles; u += 8) {
+        int32_t r[8];
+        ValT v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const bool in = u + j < num_tiles;
+            r[j] = in ? carry_row[u + j] : -1;
+            v[j] = in ? carry_val[u + j] : (ValT)0;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            more = more && r[j] == row;
+            if (more) sum += v[j];
+        }
+    }
     const ValT alpha = alpha_dev ? __ldg(alpha_dev) : (ValT)1;
     store_y(y, peers, (int64_t)row, y[row] + alpha * sum);
 }
@@ -746,18 +764,23 @@ template int launch_merge_genl<int64_t, double>(const SpmvProblem<int64_t, doubl
 
 template <typename OffT>
 int launch_partition(int32_t n_rows, OffT nnz, const OffT *Ap, int64_t tile_items, int64_t n_coords,
-                     int32_t *coords_x, cudaStream_t stream) {
+                     int32_t *coords_x, cudaStream_t stream, bool reuse) {
     if (n_coords <= 0) return SPMVB200_OK;
+    // reuse: the caller vouches that Ap still holds what it held when these coordinates were
+    // written (same pointers, same sizes, same stream) -- nothing to search again
+    const PartitionTag tag{coords_x, Ap, (int64_t)n_rows, (int64_t)nnz, tile_items, n_coords};
+    if (reuse && partition_tag_matches(stream, tag)) return SPMVB200_OK;
     const int64_t blocks = (n_coords + 255) / 256;
     merge_partition_kernel<OffT><<<(unsigned)blocks, 256, 0, stream>>>(n_rows, nnz, Ap, tile_items,
                                                                        n_coords, coords_x);
     SPMV_LAUNCH_CHECK();
+    partition_tag_store(stream, tag);
     return SPMVB200_OK;
 }
 template int launch_partition<int32_t>(int32_t, int32_t, const int32_t *, int64_t, int64_t,
-                                       int32_t *, cudaStream_t);
+                                       int32_t *, cudaStream_t, bool);
 template int launch_partition<int64_t>(int32_t, int64_t, const int64_t *, int64_t, int64_t,
-                                       int32_t *, cudaStream_t);
+                                       int32_t *, cudaStream_t, bool);
 
 // CTA size of the register-staged tile kernel: 128 threads (1020-item tiles) with 32-bit offsets,
 // 256 threads (2044-item tiles) with 64-bit offsets -- measured: 128 is 3-8 % faster on c2/c3/c4
@@ -785,7 +808,7 @@ int launch_merge(const SpmvProblem<OffT, ValT> &p) {
     SPMV_TRY(scratch_get(p.stream, SCRATCH_CARRY_VAL, (size_t)num_tiles * sizeof(ValT), &cval));
 
     SPMV_TRY(launch_partition<OffT>(p.n_rows, p.nnz, p.Ap, tile_items, num_tiles + 1,
-                                    static_cast<int32_t *>(coords), p.stream));
+                                    static_cast<int32_t *>(coords), p.stream, p.reuse_partition));
 
     // shared-memory carveout in percent of 228 KB; -1 = the driver's choice, -2 (default) = 64 KB
     // for fp32 and the driver's choice for fp64.  The driver picks 100 KB to fit every CTA the

@@ -29,6 +29,7 @@ struct ScratchBuf {
 };
 struct ScratchSet {
     ScratchBuf slot[SCRATCH_NUM_SLOTS];
+    PartitionTag last_partition{nullptr, nullptr, -1, -1, -1, -1};
 };
 std::map<std::pair<int, cudaStream_t>, ScratchSet> g_scratch;
 
@@ -110,6 +111,20 @@ int scratch_get(cudaStream_t stream, ScratchSlot slot, size_t bytes, void **out)
     }
     *out = b.ptr;
     return SPMVB200_OK;
+}
+
+bool partition_tag_matches(cudaStream_t stream, const PartitionTag &tag) {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_scratch.find({dev, stream});
+    return it != g_scratch.end() && it->second.last_partition == tag;
+}
+void partition_tag_store(cudaStream_t stream, const PartitionTag &tag) {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_scratch[{dev, stream}].last_partition = tag;
 }
 
 void scratch_release_all() {

@@ -248,8 +248,11 @@ class PowerIteration:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 self._local_events.append(ev)
                 ev[0].record()
+            # the shard never changes between steps: from the second step on the merge-path
+            # partition of the previous call is reused
             spmv_mod.spmv_ex(self.kind, m.Ap, m.Aj, m.Ax, x, y, n_cols=self.n, alpha_dev=self.alpha,
-                             y_peers=peers, multicast=self.exchange == "mc")
+                             y_peers=peers, multicast=self.exchange == "mc",
+                             static_pattern=self.step_no > 0)
             if self.step_no == 0 and self.exchange in ("p2p", "mc"):
                 # The kernels send only rows that have nonzeros to the peers; an empty row's
                 # entry must therefore already be 0 in every replica.  Buffer 1 starts zeroed;

@@ -111,13 +111,15 @@ def SpMV(kind_str, n_rows, n_cols, nnz, Ap, Aj, Ax, x, y, stream=None):
 
 
 def spmv_ex(kind_str, Ap, Aj, Ax, x, y, n_cols=None, alpha_dev=None, y_peers=(), stream=None,
-            multicast=False, semiring="plus_times", beta_dev=None):
+            multicast=False, semiring="plus_times", beta_dev=None, static_pattern=False):
     """Untyped entry (spmvb200_spmv): optional device alpha, optional peer replicas of y.
     y_peers: iterable of raw device addresses (ints), each indexed like y; with
     multicast=True it holds ONE NVLink multicast address that reaches every replica.
     semiring: "plus_times" | "min_plus" | "max_plus" | "or_and" (merge-path kernel; the fixed
     menu standing in for the reference's functor_t, merge_genl/merge_genl.cuh:19-38);
-    beta_dev: device scalar, y = alpha*A*x + beta*y (plus-times only)."""
+    beta_dev: device scalar, y = alpha*A*x + beta*y (plus-times only).
+    static_pattern: the caller vouches that Ap is unchanged since the previous call on this
+    stream, so the merge-path tile coordinates of that call are reused (never on a first call)."""
     _check_tensors(Ap, Aj, Ax, x, y)
     if kind_str not in KIND_IDS:
         raise SpMVKindError(f'SpMV kind "{kind_str}" is NOT SUPPROT')
@@ -133,6 +135,7 @@ def spmv_ex(kind_str, Ap, Aj, Ax, x, y, n_cols=None, alpha_dev=None, y_peers=(),
     a.alpha_dev = alpha_dev.data_ptr() if alpha_dev is not None else None
     a.beta_dev = beta_dev.data_ptr() if beta_dev is not None else None
     a.semiring = _lib.SEMIRINGS[semiring]
+    a.flags = _lib.FLAG_STATIC_PATTERN if static_pattern else 0
     peers = list(y_peers)
     if multicast and len(peers) != 1:
         raise ValueError("multicast=True takes exactly one address")

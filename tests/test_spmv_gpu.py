@@ -511,3 +511,38 @@ def test_neighbouring_memory_is_neither_used_nor_written(case, kind):
         torch.cuda.synchronize()
         assert np.array_equal(dy.cpu().numpy(), cpu.spmv_semiring(Ap, Aj, Ax, x, "min_plus"))
         assert bool((torch.cat([ybuf[:64], ybuf[64 + n_rows:]]) == 12345.0).all())
+
+
+def test_static_pattern_flag_reuses_and_never_goes_stale():
+    """SPMVB200_FLAG_STATIC_PATTERN: same results with the flag as without; a call WITHOUT the
+    flag always searches again, so a caller that changes Ap in place and drops the flag once is
+    safe; unknown flag bits are rejected."""
+    from spmv_samples_b200 import _lib, spmv
+    Ap, Aj, Ax = g.rmat(13, 16, 5)
+    n = Ap.shape[0] - 1
+    x = g.gen_x(7, n)
+    dAp, dAj, dAx, dx = dev(Ap), dev(Aj), dev(Ax), dev(x)
+    y0 = torch.empty(n, device="cuda")
+    y1 = torch.empty(n, device="cuda")
+    launches = []
+    for flag in (False, True, True):
+        before = spmv.launch_count()
+        spmv.spmv_ex("merge", dAp, dAj, dAx, dx, y1 if flag else y0, static_pattern=flag)
+        launches.append(spmv.launch_count() - before)
+    torch.cuda.synchronize()
+    assert torch.equal(y0, y1)
+    assert launches[1] == launches[0] - 1 and launches[2] == launches[1]     # the search is skipped
+    # another matrix of the same shape in the SAME buffers: dropping the flag once is enough
+    lens = np.diff(Ap).astype(np.int64)
+    np.random.default_rng(3).shuffle(lens)                                   # same n_rows, same nnz
+    Ap3 = np.zeros(n + 1, dtype=Ap.dtype)
+    np.cumsum(lens, out=Ap3[1:])
+    dAp.copy_(torch.from_numpy(Ap3).cuda())
+    spmv.spmv_ex("merge", dAp, dAj, dAx, dx, y0, static_pattern=False)
+    spmv.spmv_ex("merge", dAp, dAj, dAx, dx, y1, static_pattern=True)
+    torch.cuda.synchronize()
+    assert torch.equal(y0, y1)
+    assert_within_tolerance(y1.cpu().numpy(), Ap3, Aj, Ax, x, "static pattern after in-place change")
+    a = _lib.Args()
+    a.flags = 2
+    assert _lib.lib().spmvb200_spmv(C.byref(a)) == 1
