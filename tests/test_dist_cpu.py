@@ -139,3 +139,20 @@ def test_rebalance_targets_moves_boundaries_towards_equal_time():
     # degenerate inputs
     assert spmv.rebalance_targets([0, 10], [3.0]) == []
     assert spmv.rebalance_targets(cost, [0.0, 0.0, 0.0, 0.0]) == [1000, 2000, 3000]
+
+
+def test_host_buffer_front_ends_refuse_to_run_without_cuda():
+    """No CPU fallback in the product: the sharded host-buffer call and the power iteration both
+    raise when there is no CUDA device (the GPU suite covers the real path)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("this check is for the CPU-only container")
+    from spmv_samples_b200 import generate
+    from spmv_samples_b200.dist import PowerIteration, Shard, ShardedHostSpMV
+    Ap = torch.tensor([0, 1, 2], dtype=torch.int32)
+    csr = generate.Csr(2, 2, 2, Ap, torch.tensor([0, 1], dtype=torch.int32), torch.ones(2), "tiny")
+    shard = Shard(0, 1, 0, 2, 0, 2, [0, 2], csr)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ShardedHostSpMV(shard, 2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        PowerIteration(shard, 2)
