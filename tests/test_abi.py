@@ -81,3 +81,30 @@ def test_product_never_imports_the_oracle():
                             or "libspmv_ref" in text:
                         bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_argument_validation_needs_no_device(built_lib):
+    """Argument checks come before any CUDA call, so they can be exercised here: the weighted
+    split search, the untyped entry's flag word, the SpMM shape checks."""
+    import ctypes as C
+    from spmv_samples_b200 import _lib
+    L = built_lib
+    t = (C.c_int64 * 2)(5, 9)
+    out = (C.c_int64 * 2)(-1, -1)
+    ap = (C.c_int32 * 4)(0, 1, 2, 3)
+    f = L.spmvb200_rows_at_cost_o32
+    assert f(3, ap, 1, 0, 2, t, out, None) == 1                 # w_den < 1
+    assert f(3, ap, -1, 1, 2, t, out, None) == 1                # w_num < 0
+    assert f(3, ap, (1 << 20) + 1, 1, 2, t, out, None) == 4     # weight out of the int64-safe range
+    assert f(3, ap, 1, 1, 0, None, None, None) == 0             # nothing asked
+    assert f(3, ap, 1, 1, 2, None, out, None) == 1              # targets missing
+    neg = (C.c_int64 * 2)(5, -1)
+    assert f(3, ap, 1, 1, 2, neg, out, None) == 1               # negative cost
+    assert f(0, None, 1, 1, 2, t, out, None) == 0 and list(out) == [0, 0]   # no rows: row 0 for every target
+    a = _lib.Args()
+    a.flags = 4
+    assert L.spmvb200_spmv(C.byref(a)) == 1                     # unknown flag bit
+    s = _lib.SpmmArgs()
+    s.k = 3
+    assert L.spmvb200_spmm(C.byref(s)) == 4                     # k must be 2, 4 or 8
+    assert L.spmvb200_matrix_wait(None, 0) == 1 and L.spmvb200_matrix_submit_host(None, 0, 9, None, None) == 1
