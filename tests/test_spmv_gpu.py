@@ -546,3 +546,37 @@ def test_static_pattern_flag_reuses_and_never_goes_stale():
     a = _lib.Args()
     a.flags = 2
     assert _lib.lib().spmvb200_spmv(C.byref(a)) == 1
+
+
+# ------------------------------------------------------------------ the dynamic-row kernel's tiers
+def _light_tier_cases():
+    short = [4] * 256
+    heavy = [100] * 256                      # 25.6K nonzeros in a claim of 256 rows: tier 2
+    mega = [3] * 100 + [20011] + [0] * 155   # one row beyond 8K nonzeros inside a heavy claim: tier 3
+    return {
+        "heavy_first_and_last": heavy + short * 40 + heavy,
+        "heavy_partial_last_block": short * 30 + [300] * 100,           # n_rows not a multiple of the claim
+        "mega_rows_first_middle_last": mega + short * 20 + mega + short * 20 + mega,
+        "every_block_heavy": heavy * 12,
+        "mega_only": [40000, 0, 0, 9000, 12000] + [0] * 300,
+    }
+
+
+@pytest.mark.parametrize("off,val", [(np.int32, np.float32), (np.int64, np.float64)])
+@pytest.mark.parametrize("case", sorted(_light_tier_cases()))
+def test_light_tiers(case, off, val):
+    """Blocks of rows that are heavy (more than 16K nonzeros in one claim), rows long enough for
+    the CTA pass, at the first, a middle and the last claim of the matrix, with a short last claim;
+    run twice: the result must not depend on which warp drew what."""
+    from spmv_samples_b200 import spmv
+    lens = _light_tier_cases()[case]
+    Ap, Aj, Ax = _csr(lens, 5000, seed=11, dtype=val, off=off)
+    x = g.gen_x(31, 5000, val)
+    spmv.set_option("light_rows_per_claim", 256)
+    try:
+        y1 = run_kind("light", Ap, Aj, Ax, x, 5000)
+        y2 = run_kind("light", Ap, Aj, Ax, x, 5000)
+    finally:
+        spmv.set_option("light_rows_per_claim", 0)
+    assert_within_tolerance(y1, Ap, Aj, Ax, x, f"light tiers {case}")
+    assert np.array_equal(y1, y2)
