@@ -146,3 +146,86 @@ def test_blank_lines_and_case_insensitive_banner(shim, tmp_path):
     open(p, "w").write("%%MatrixMarket MATRIX Coordinate Real GENERAL\n%c\n\n2 3 2\n\n1 3 1e0\n2 1 -2.5E+0\n")
     rc, (n, m, Ap, Aj, Ax) = load(shim, p)
     assert (n, m) == (2, 3) and Ap.tolist() == [0, 1, 2] and Aj.tolist() == [2, 0] and Ax.tolist() == [1.0, -2.5]
+
+
+def _write_big_mtx(path, n, nnz, seed, field="real", scheme="general", fmt="%d %d %.17g"):
+    rng = np.random.default_rng(seed)
+    r = rng.integers(1, n + 1, nnz)
+    c = rng.integers(1, n + 1, nnz)
+    if scheme != "general":
+        r, c = np.maximum(r, c), np.minimum(r, c)
+    v = rng.uniform(-3, 3, nnz) * 10.0 ** rng.integers(-30, 30, nnz)   # exercises the strtod fallback too
+    with open(path, "w") as f:
+        f.write(f"%%MatrixMarket matrix coordinate {field} {scheme}\n% big\n{n} {n} {nnz}\n")
+        if field == "pattern":
+            np.savetxt(f, np.column_stack([r, c]), fmt="%d %d")
+        else:
+            np.savetxt(f, np.column_stack([r, c, v]), fmt=fmt)
+
+
+@pytest.mark.skipif(not cpu.have_ref(), reason="oracle/_ref not built (no /root/reference here)")
+@pytest.mark.parametrize("threads", ["1", "3", "8"])
+@pytest.mark.parametrize("field,scheme", [("real", "general"), ("real", "symmetric"), ("pattern", "general")])
+def test_threaded_paths_match_reference_loader(shim, tmp_path, monkeypatch, field, scheme, threads):
+    """Files large enough for the line-parallel parser and the threaded ToCsr (>= 256 KB, >= 2^17
+    entries), with 1, 3 and 8 threads: the arrays must be the reference loader's, bit for bit."""
+    monkeypatch.setenv("SPMV_LOADER_THREADS", threads)
+    path = str(tmp_path / "big.mtx")
+    _write_big_mtx(path, 5000, 150_000, 3, field, scheme)
+    rc, out = load(shim, path)
+    assert rc == 0, out
+    n_rows, n_cols, Ap, Aj, Ax = out
+    rn, rc_, rAp, rAj, rAx = cpu.ref_load_mtx(path)
+    assert (n_rows, n_cols) == (rn, rc_)
+    assert np.array_equal(Ap, rAp) and np.array_equal(Aj, rAj) and np.array_equal(Ax, rAx)
+    # 64-bit offsets, fp64 values through the same paths
+    rc, out = load(shim, path, wide=True)
+    assert rc == 0 and np.array_equal(out[2], rAp) and np.array_equal(out[3], rAj)
+    assert np.array_equal(out[4].astype(np.float32), rAx)
+
+
+@pytest.mark.skipif(not cpu.have_ref(), reason="oracle/_ref not built (no /root/reference here)")
+def test_unusual_layouts_fall_back_to_the_tokenizer(shim, tmp_path, monkeypatch):
+    """Two entries on one line, an entry split over two lines, trailing lines after the last
+    entry: the per-line parser declines and the sequential tokenizer gives the reference's result."""
+    monkeypatch.setenv("SPMV_LOADER_THREADS", "4")
+    rng = np.random.default_rng(8)
+    n, nnz = 3000, 40_000
+    r, c, v = rng.integers(1, n + 1, nnz), rng.integers(1, n + 1, nnz), rng.uniform(-1, 1, nnz)
+    path = str(tmp_path / "odd.mtx")
+    with open(path, "w") as f:
+        f.write(f"%%MatrixMarket matrix coordinate real general\n{n} {n} {nnz}\n")
+        i = 0
+        while i < nnz:
+            if i % 7 == 0 and i + 1 < nnz:      # two entries on one line
+                f.write(f"{r[i]} {c[i]} {v[i]:.9g}   {r[i+1]} {c[i+1]} {v[i+1]:.9g}\n")
+                i += 2
+            elif i % 11 == 0:                    # one entry over two lines
+                f.write(f"{r[i]} {c[i]}\n   {v[i]:.9g}\n")
+                i += 1
+            else:
+                f.write(f"{r[i]} {c[i]} {v[i]:.9g}\n")
+                i += 1
+        f.write("1 1 99\n2 2 99\n")             # beyond the announced count: ignored
+    rc, out = load(shim, path)
+    assert rc == 0, out
+    rn, rc_, rAp, rAj, rAx = cpu.ref_load_mtx(path)
+    assert np.array_equal(out[2], rAp) and np.array_equal(out[3], rAj) and np.array_equal(out[4], rAx)
+
+
+def test_errors_come_from_one_place_whatever_the_size(shim, tmp_path, monkeypatch):
+    """A zero index deep inside a large file: same exception text as in a small one."""
+    monkeypatch.setenv("SPMV_LOADER_THREADS", "4")
+    path = str(tmp_path / "zero.mtx")
+    with open(path, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real general\n1000 1000 60000\n")
+        for i in range(60000):
+            f.write(f"{1 + i % 1000} {0 if i == 43210 else 1 + (7 * i) % 1000} 1.5\n")
+    rc, msg = load(shim, path)
+    assert rc == 100 and "zero-indexed" in msg
+    with open(path, "w") as f:                    # short file
+        f.write("%%MatrixMarket matrix coordinate real general\n1000 1000 60000\n")
+        for i in range(59000):
+            f.write(f"{1 + i % 1000} {1 + (7 * i) % 1000} 1.5\n")
+    rc, msg = load(shim, path)
+    assert rc == 100 and "Could not read weighted edge" in msg
