@@ -259,9 +259,11 @@ struct cursor {
 // One entry per line, parsed by several threads.  `body` is everything after the size line.
 // Returns false -- and the caller falls back to the sequential tokenizer -- if the region does
 // not look like that: fewer non-blank lines than entries, a line that is not exactly
-// "row col [value]", or a zero index (so that errors are reported by one code path only).
+// "row col [value]", a zero index or an index beyond the header's dimensions (so that errors
+// are reported by one code path only).
 template <typename index_t, typename value_t>
 inline bool parse_entries_by_line(const char *begin, const char *end, std::size_t entries, bool has_value,
+                                  std::size_t n_rows, std::size_t n_cols,
                                   std::vector<index_t> &I, std::vector<index_t> &J, std::vector<value_t> &V,
                                   int n_threads) {
     const std::size_t bytes = (std::size_t)(end - begin);
@@ -317,6 +319,8 @@ inline bool parse_entries_by_line(const char *begin, const char *end, std::size_
             d0 = q;
             while (q < stop && *q >= '0' && *q <= '9') c = c * 10 + (std::size_t)(*q++ - '0');
             if (q == d0 || q - d0 > 18 || r == 0 || c == 0) { bad[(size_t)t] = 1; return; }
+            // an index beyond the header's dimensions: the sequential path reports it
+            if (r > n_rows || c > n_cols) { bad[(size_t)t] = 1; return; }
             double w = 1.0;
             if (has_value) {
                 if (q >= stop || !is_blank(*q)) { bad[(size_t)t] = 1; return; }
@@ -424,7 +428,7 @@ int TryLoadCoo(const std::string &filename, coo_t<index_t, offset_t, value_t> &c
         body = nl ? nl + 1 : cur.end;
     }
     const bool by_line = h.entries > 0 && mm_detail::parse_entries_by_line<index_t, value_t>(
-                                              body, cur.end, h.entries, h.data != pattern, I0, J0, V0, n_threads);
+                                              body, cur.end, h.entries, h.data != pattern, h.rows, h.cols, I0, J0, V0, n_threads);
     if (by_line && !mirror) {
         I.swap(I0);
         J.swap(J0);
@@ -475,6 +479,10 @@ int TryLoadCoo(const std::string &filename, coo_t<index_t, offset_t, value_t> &c
                                                   : "Could not read weighted edge from market file");
         throw_if_exception(r == 0, "Market file is zero-indexed");
         throw_if_exception(c == 0, "Market file is zero-indexed");
+        // The reference stores such an entry unchecked (load.hpp:330-331) and its ToCsr then writes
+        // past row_offsets (load.hpp:443-445); here it is an error before any array is indexed.
+        throw_if_exception(r > h.rows, "Market file row index exceeds the number of rows");
+        throw_if_exception(c > h.cols, "Market file column index exceeds the number of columns");
         const index_t ri = (index_t)(r - 1), ci = (index_t)(c - 1);
         const value_t v = h.data == pattern ? (value_t)1.0 : (value_t)w;
         I.push_back(ri);

@@ -11,6 +11,7 @@
 
 #include "common.cuh"
 #include "spmv/auto_select.hpp"
+#include "spmv/csr_stream.hpp"
 #include "spmv/csr_vector.hpp"
 #include "spmv/cusparse_baseline.hpp"
 #include "spmv/dynamic_rows.hpp"
@@ -18,14 +19,23 @@
 #include "spmv/merge_generalized.hpp"
 #include "spmv/merge_path.hpp"
 
-/// SPMV kind strings and its function
+/// SPMV kind strings and its function.  The second block keeps every label of the reference's
+/// table (spmv.h:18-27) working on a reference-style command line: each names the kernel here
+/// that replaces the reference kernel of that label.
 #define SPMV_KINDS                                                             \
     X("merge", SpMV_merge_path)                                                \
     X("merge_genl", SpMV_merge_generalized)                                    \
     X("vector", SpMV_csr_vector)                                               \
     X("light", SpMV_dynamic_rows)                                              \
+    X("stream", SpMV_csr_stream)                                               \
     X("auto", SpMV_auto_select)                                                \
-    X("cusparse", SpMV_cusparse)
+    X("cusparse", SpMV_cusparse)                                               \
+    X("cusp", SpMV_csr_vector)                                                 \
+    X("cusp1", SpMV_csr_vector)                                                \
+    X("cusp2", SpMV_csr_vector)                                                \
+    X("light_vec", SpMV_dynamic_rows)                                          \
+    X("light_warp", SpMV_dynamic_rows)                                         \
+    X("cub_merge", SpMV_merge_path)
 
 template <typename index_t, typename offset_t, typename mat_value_t,
           typename vec_x_value_t, typename vec_y_value_t>

@@ -48,6 +48,7 @@ struct check_types {
 SPMV_ABI_KIND(merge)
 SPMV_ABI_KIND(vector)
 SPMV_ABI_KIND(light)
+SPMV_ABI_KIND(stream)
 SPMV_ABI_KIND(auto)
 SPMV_ABI_KIND(cusparse)
 #undef SPMV_ABI_KIND

@@ -18,7 +18,9 @@
  * Contract:
  *   - all five arrays are DEVICE pointers owned by the caller; Ap, Aj, Ax, x are
  *     read-only; y (n_rows entries) is fully overwritten: y = A*x (alpha = 1, beta = 0),
- *     empty rows give 0; n_rows == 0 or n_cols == 0 is a no-op;
+ *     empty rows give 0; n_rows == 0 is a no-op; n_cols == 0 (then nnz must be 0) writes
+ *     y = 0 like any other matrix of empty rows -- the reference returns without touching y
+ *     there (merge_based/dispatch_spmv_orig.cuh:564-570), which leaves y stale;
  *   - index type is int32; offsets are int32 (o32) or int64 (o64); values, x and y share
  *     one type, float (f32) or double (f64);
  *   - Ap, Aj, Ax must be 16-byte aligned (cudaMalloc gives 256); checked, not assumed:
@@ -62,7 +64,8 @@ enum {
     SPMVB200_KIND_VECTOR = 1, /* "vector": CSR-vector, sub-warp per row, shuffle reduce   */
     SPMVB200_KIND_LIGHT = 2,  /* "light":  LightSpMV-style dynamic row hand-out (atomics) */
     SPMVB200_KIND_AUTO = 3,   /* "auto":   host selector from cached row statistics       */
-    SPMVB200_KIND_CUSPARSE = 4 /* "cusparse": cusparseSpMV baseline, setup hoisted         */
+    SPMVB200_KIND_CUSPARSE = 4, /* "cusparse": cusparseSpMV baseline, setup hoisted        */
+    SPMVB200_KIND_STREAM = 5  /* "stream": CSR-stream, TMA-staged row tiles, thread per row */
 };
 
 SPMVB200_API const char *spmvb200_status_string(int status);
@@ -90,6 +93,10 @@ SPMVB200_DECLARE_KIND(merge)
 SPMVB200_DECLARE_KIND(vector)
 /* replaces SpMV_light_vector / SpMV_light_warp (reference/include/spmv/LightSpMV.cuh:379,399) */
 SPMVB200_DECLARE_KIND(light)
+/* the short-regular-row case of SpMV_cusp_* (THREADS_PER_VECTOR = 2 / 4,
+ * reference/include/spmv/cusp/cusp.cuh:189-203): persistent CTAs, row tiles staged in shared
+ * memory with TMA bulk copies, one thread per row */
+SPMVB200_DECLARE_KIND(stream)
 /* new: per-matrix selector (BASELINE.json north_star "host-side selector") */
 SPMVB200_DECLARE_KIND(auto)
 /* replaces SpMV_cusparse (reference/include/spmv/cusparse.cuh:37-88); comparison baseline */
@@ -231,6 +238,17 @@ SPMVB200_API int64_t spmvb200_get_option(const char *name);
 SPMVB200_API int64_t spmvb200_launch_count(void);
 /* drop cached scratch / statistics (all devices) */
 SPMVB200_API void spmvb200_release_cache(void);
+
+/* The hot-x plan of the merge-path kernel (csrc/hotx.cu): for an x far longer than the TLB and L2
+ * reach (option "hot_x_min_bytes", 256 MB) and a caller that passes SPMVB200_FLAG_STATIC_PATTERN,
+ * the library keeps a copy of Aj in which the most frequent columns are renumbered into one dense
+ * array x_hot (refilled from x before every SpMV).  Products and their order are unchanged: y is
+ * bit-identical.  Costs nnz * 4 bytes of device memory, built at the first flagged call.  Reports
+ * what was built for this Aj on the current device (0 columns = no plan).  The flag therefore
+ * vouches for Aj as well as Ap.  Nothing in the reference corresponds (it gathers x[Aj[k]] as is,
+ * merge_based/agent_spmv_orig.cuh:474-506). */
+SPMVB200_API int spmvb200_hot_x_info(const int32_t *Aj, int64_t *hot_columns, double *hot_share,
+                                     double *build_ms);
 
 /* ---- host-buffer convenience: the end-to-end call --------------------------------------
  * A CSR matrix uploaded once (as reference/main.cu:55-69 does), then y = A*x with x and y

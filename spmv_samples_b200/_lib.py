@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("SPMVB200_LIB") or os.path.join(_PKG, "libspmvb200.so"
 CSRC = os.path.join(_PKG, "csrc")
 
 OK = 0
-KIND_MERGE, KIND_VECTOR, KIND_LIGHT, KIND_AUTO, KIND_CUSPARSE = 0, 1, 2, 3, 4
+KIND_MERGE, KIND_VECTOR, KIND_LIGHT, KIND_AUTO, KIND_CUSPARSE, KIND_STREAM = 0, 1, 2, 3, 4, 5
 FLAG_STATIC_PATTERN = 1   # SPMVB200_FLAG_STATIC_PATTERN
 SEMIRINGS = {"plus_times": 0, "min_plus": 1, "max_plus": 2, "or_and": 3}
 MAX_PEERS = 8
@@ -136,7 +136,9 @@ def lib() -> C.CDLL:
     L.spmvb200_ipc_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
     L.spmvb200_ipc_close.argtypes = [C.c_void_p]
     L.spmvb200_release_cache.restype = None
-    for kind in ("merge", "vector", "light", "auto", "cusparse"):
+    L.spmvb200_hot_x_info.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double),
+                                      C.POINTER(C.c_double)]
+    for kind in ("merge", "vector", "light", "stream", "auto", "cusparse"):
         for otag, otype in (("o32", C.c_int32), ("o64", C.c_int64)):
             for vtag in ("f32", "f64"):
                 fn = getattr(L, f"spmvb200_{kind}_i32_{otag}_{vtag}")

@@ -58,7 +58,7 @@ int apply_carveout(const void *kernel, int64_t percent);
 // Per-(device, stream) scratch that survives across calls, grown on demand.
 // Slots keep independent buffers so a kernel can hold several at once.
 enum ScratchSlot { SCRATCH_COORDS = 0, SCRATCH_CARRY_ROW, SCRATCH_CARRY_VAL, SCRATCH_COUNTER,
-                   SCRATCH_STATS, SCRATCH_MISC, SCRATCH_SPMM_X, SCRATCH_SPMM_Y, SCRATCH_NUM_SLOTS };
+                   SCRATCH_STATS, SCRATCH_MISC, SCRATCH_SPMM_X, SCRATCH_SPMM_Y, SCRATCH_XHOT, SCRATCH_NUM_SLOTS };
 int scratch_get(cudaStream_t stream, ScratchSlot slot, size_t bytes, void **out);
 
 // What the last merge-path partition launched on a (device, stream) wrote, and where: lets a
@@ -121,6 +121,7 @@ template <typename OffT, typename ValT>
 int launch_merge_genl(const SpmvProblem<OffT, ValT> &p, int semiring, const ValT *beta_dev);
 template <typename OffT, typename ValT> int launch_vector(const SpmvProblem<OffT, ValT> &p, int width);
 template <typename OffT, typename ValT> int launch_light(const SpmvProblem<OffT, ValT> &p, int width);
+template <typename OffT, typename ValT> int launch_stream(const SpmvProblem<OffT, ValT> &p);
 template <typename OffT, typename ValT> int launch_cusparse(const SpmvProblem<OffT, ValT> &p);
 template <typename OffT, typename ValT> int launch_auto(const SpmvProblem<OffT, ValT> &p);
 template <typename OffT>
@@ -134,6 +135,25 @@ template <typename OffT, typename ValT>
 int launch_spmm(int k, int32_t n_rows, int32_t n_cols, OffT nnz, const OffT *Ap, const int32_t *Aj,
                 const ValT *Ax, const ValT *X, int64_t ldx, ValT *Y, int64_t ldy, const ValT *alpha_dev,
                 cudaStream_t stream);
+
+// The hot part of x, compacted (hotx.cu): a per-matrix plan holding a remapped copy of Aj (hot
+// column c stored as 0x80000000 | rank) and the list of hot columns; x_hot lives in the
+// per-stream scratch (calls on different streams may share a plan) and is refilled from x by
+// hot_gather before every SpMV that uses the plan.
+struct HotPlan {
+    const int32_t *Aj2 = nullptr;
+    const int32_t *hot_cols = nullptr;
+    int64_t K = 0;
+    uint32_t threshold = 0;   // a column is hot when it occurs at least this often
+    double hot_share = 0.0;   // fraction of the gathers that go to hot columns
+    double build_ms = 0.0;
+};
+int hot_plan_get(const int32_t *Aj, int64_t nnz, int32_t n_cols, size_t val_bytes, cudaStream_t stream,
+                 bool may_build, const HotPlan **out);
+template <typename ValT> int hot_gather(const HotPlan &plan, const ValT *x, cudaStream_t stream, const ValT **x_hot);
+void hot_plan_clear();
+void hot_plan_drop(const int32_t *Aj);
+const HotPlan *hot_plan_peek(const int32_t *Aj);  // the plan built for this Aj on the current device, or nullptr
 
 // Launch attribute helper: optional L2 access-policy window over x (option "l2_window").
 struct LaunchCfg {
@@ -205,33 +225,36 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint3
 // SPMV_GATHER_MODE selects the load flavour at compile time (ablation; default 0):
 //   0  ld.global.nc + L2::cache_hint(evict_last)      1  ld.global.cg (bypass L1)
 //   2  ld.global.nc.L1::no_allocate + L2 hint         3  plain ld.global.nc
+//   4  ld.global.nc.L2::128B (whole line on an L2 miss)   5  4 + evict_last hint
+//   6  ld.global.nc.L2::256B                              7  ld.global.nc.L2::64B
 #ifndef SPMV_GATHER_MODE
 #define SPMV_GATHER_MODE 0
 #endif
+#if SPMV_GATHER_MODE == 0
+#define SPMV_GATHER_ASM(T, C) "ld.global.nc.L2::cache_hint." T " %0, [%1], %2;" : "=" C(v) : "l"(p), "l"(policy)
+#elif SPMV_GATHER_MODE == 1
+#define SPMV_GATHER_ASM(T, C) "ld.global.cg." T " %0, [%1];" : "=" C(v) : "l"(p)
+#elif SPMV_GATHER_MODE == 2
+#define SPMV_GATHER_ASM(T, C) "ld.global.nc.L1::no_allocate.L2::cache_hint." T " %0, [%1], %2;" : "=" C(v) : "l"(p), "l"(policy)
+#elif SPMV_GATHER_MODE == 3
+#define SPMV_GATHER_ASM(T, C) "ld.global.nc." T " %0, [%1];" : "=" C(v) : "l"(p)
+#elif SPMV_GATHER_MODE == 4
+#define SPMV_GATHER_ASM(T, C) "ld.global.nc.L2::128B." T " %0, [%1];" : "=" C(v) : "l"(p)
+#elif SPMV_GATHER_MODE == 5
+#define SPMV_GATHER_ASM(T, C) "ld.global.nc.L2::cache_hint.L2::128B." T " %0, [%1], %2;" : "=" C(v) : "l"(p), "l"(policy)
+#elif SPMV_GATHER_MODE == 6
+#define SPMV_GATHER_ASM(T, C) "ld.global.nc.L2::256B." T " %0, [%1];" : "=" C(v) : "l"(p)
+#else
+#define SPMV_GATHER_ASM(T, C) "ld.global.nc.L2::64B." T " %0, [%1];" : "=" C(v) : "l"(p)
+#endif
 __device__ __forceinline__ float ldg_hint(const float *p, uint64_t policy) {
     float v;
-#if SPMV_GATHER_MODE == 0
-    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(policy));
-#elif SPMV_GATHER_MODE == 1
-    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
-#elif SPMV_GATHER_MODE == 2
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(policy));
-#else
-    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
-#endif
+    asm volatile(SPMV_GATHER_ASM("f32", "f"));
     return v;
 }
 __device__ __forceinline__ double ldg_hint(const double *p, uint64_t policy) {
     double v;
-#if SPMV_GATHER_MODE == 0
-    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy));
-#elif SPMV_GATHER_MODE == 1
-    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
-#elif SPMV_GATHER_MODE == 2
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy));
-#else
-    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
-#endif
+    asm volatile(SPMV_GATHER_ASM("f64", "d"));
     return v;
 }
 

@@ -308,14 +308,17 @@ template <> struct LoadVals<double> {
     }
 };
 
-template <int BLOCK, bool HAS_PEERS, typename OffT, typename ValT>
+// HOT: Aj is the remapped copy of a hot-x plan (hotx.cu): an index with the top bit set is a rank
+// into the dense copy of the hot columns' x; x_hot_biased = x_hot - 2^31 elements, so that either
+// base + (uint32) index is the address.
+template <int BLOCK, bool HAS_PEERS, bool HOT, typename OffT, typename ValT>
 __device__ __forceinline__ void
 merge_tile_reg_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
                     const int32_t *__restrict__ Aj, const ValT *__restrict__ Ax,
                     const ValT *__restrict__ x, ValT *__restrict__ y,
                     const ValT *__restrict__ alpha_dev, const PeerOut &peers,
                     const int32_t *__restrict__ coords_x, int32_t *__restrict__ carry_row,
-                    ValT *__restrict__ carry_val) {
+                    ValT *__restrict__ carry_val, const ValT *__restrict__ x_hot_biased) {
     constexpr int IPT = kMergeIPT;
     constexpr int SLOTS = BLOCK * IPT;
     constexpr int TILE = SLOTS - 4;  // path items per tile
@@ -385,7 +388,8 @@ merge_tile_reg_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
 #pragma unroll
         for (int k = 0; k < IPT; ++k) {
             const int i = slot0 + k - shift;
-            xv[k] = (i >= 0 && i < Z) ? ldg_hint(x + c[k], pol_x) : (ValT)0;
+            const ValT *src = HOT ? (c[k] < 0 ? x_hot_biased : x) + (uint32_t)c[k] : x + c[k];
+            xv[k] = (i >= 0 && i < Z) ? ldg_hint(src, pol_x) : (ValT)0;
         }
 #pragma unroll
         for (int k = 0; k < IPT; ++k) {
@@ -472,13 +476,20 @@ merge_tile_reg_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
     int32_t *__restrict__ carry_row, ValT *__restrict__ carry_val
 template <int BLOCK, bool HAS_PEERS, typename OffT, typename ValT>
 __global__ void __launch_bounds__(BLOCK, 2048 / BLOCK) merge_tile_reg_kernel_occ8(MERGE_REG_KERNEL_ARGS) {
-    merge_tile_reg_body<BLOCK, HAS_PEERS, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers, coords_x,
-                                               carry_row, carry_val);
+    merge_tile_reg_body<BLOCK, HAS_PEERS, false, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers,
+                                                             coords_x, carry_row, carry_val, nullptr);
 }
 template <int BLOCK, bool HAS_PEERS, typename OffT, typename ValT>
 __global__ void __launch_bounds__(BLOCK) merge_tile_reg_kernel(MERGE_REG_KERNEL_ARGS) {
-    merge_tile_reg_body<BLOCK, HAS_PEERS, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers, coords_x,
-                                               carry_row, carry_val);
+    merge_tile_reg_body<BLOCK, HAS_PEERS, false, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers,
+                                                             coords_x, carry_row, carry_val, nullptr);
+}
+// the hot-x variant: Aj is the plan's remapped copy
+template <int BLOCK, bool HAS_PEERS, typename OffT, typename ValT>
+__global__ void __launch_bounds__(BLOCK)
+merge_tile_hot_kernel(MERGE_REG_KERNEL_ARGS, const ValT *__restrict__ x_hot_biased) {
+    merge_tile_reg_body<BLOCK, HAS_PEERS, true, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers,
+                                                            coords_x, carry_row, carry_val, x_hot_biased);
 }
 #undef MERGE_REG_KERNEL_ARGS
 
@@ -683,7 +694,7 @@ merge_tile_genl_kernel(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
         const int b = b64 > 0 ? (int)b64 : 0;
         const ValT sum = q > b ? scan[q - 1] : ident;
         ValT out = S::kLinear ? alpha * sum : sum;
-        if (S::kLinear && beta_dev) out += beta * y[(int64_t)sx + j];
+        if (S::kLinear && beta_dev && beta != (ValT)0) out += beta * y[(int64_t)sx + j];  // beta = 0: y is not read (BLAS)
         // beta makes every row's value depend on the old y, and a non-zero identity makes empty
         // rows non-zero: in both cases every row goes to the peers
         store_y_nonempty(y, peers, (int64_t)sx + j, out, q > b || beta_dev != nullptr || !S::kLinear);
@@ -844,16 +855,40 @@ int launch_merge(const SpmvProblem<OffT, ValT> &p) {
         // gets 32 registers from ptxas unprompted and spills under the bound; fp64 needs 64
         constexpr bool occ = sizeof(ValT) == 4 && sizeof(OffT) == 4;
         const bool has_peers = p.peers.n != 0;
-        auto kernel = has_peers ? merge_tile_reg_kernel<RB, true, OffT, ValT>      // 40 regs, no spill
-                      : occ     ? merge_tile_reg_kernel_occ8<RB, false, OffT, ValT>
-                                : merge_tile_reg_kernel<RB, false, OffT, ValT>;
-        SPMV_TRY(apply_carveout(reinterpret_cast<const void *>(kernel), carveout));
+        // hot-x plan (hotx.cu): by default only for a caller that vouches for an unchanged matrix
+        // and an x far longer than the TLB and the L2 reach
+        const int64_t hot_opt = option_get("hot_x", -1);
+        const bool want_hot = hot_opt > 0 || (hot_opt < 0 && p.reuse_partition &&
+                              (int64_t)p.n_cols * (int64_t)sizeof(ValT) > option_get("hot_x_min_bytes", 256ll << 20));
+        const HotPlan *hot = nullptr;
+        if (want_hot) SPMV_TRY(hot_plan_get(p.Aj, (int64_t)p.nnz, p.n_cols, sizeof(ValT), p.stream, true, &hot));
+        // a call without the flag says "this may be a new matrix": a plan left at this address by
+        // an earlier one must not survive it
+        else if (hot_opt < 0 && !p.reuse_partition) hot_plan_drop(p.Aj);
         make_launch_cfg(lc, dim3((unsigned)num_tiles), dim3(RB), 0, p.stream, p.x,
                         (size_t)p.n_cols * sizeof(ValT));
-        KernelTimerScope timed(p.stream);
-        SPMV_CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, kernel, p.n_rows, p.nnz, p.Ap, p.Aj, p.Ax, p.x, p.y,
-                                         p.alpha_dev, p.peers, (const int32_t *)coords,
-                                         static_cast<int32_t *>(crow), static_cast<ValT *>(cval)));
+        if (hot) {
+            const ValT *x_hot = nullptr;
+            SPMV_TRY(hot_gather<ValT>(*hot, p.x, p.stream, &x_hot));
+            auto kernel = has_peers ? merge_tile_hot_kernel<RB, true, OffT, ValT>
+                                    : merge_tile_hot_kernel<RB, false, OffT, ValT>;
+            SPMV_TRY(apply_carveout(reinterpret_cast<const void *>(kernel), carveout));
+            const ValT *x_hot_biased = x_hot - ((ptrdiff_t)1 << 31);
+            KernelTimerScope timed(p.stream);
+            SPMV_CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, kernel, p.n_rows, p.nnz, p.Ap, hot->Aj2, p.Ax, p.x, p.y,
+                                             p.alpha_dev, p.peers, (const int32_t *)coords,
+                                             static_cast<int32_t *>(crow), static_cast<ValT *>(cval),
+                                             x_hot_biased));
+        } else {
+            auto kernel = has_peers ? merge_tile_reg_kernel<RB, true, OffT, ValT>      // 40 regs, no spill
+                          : occ     ? merge_tile_reg_kernel_occ8<RB, false, OffT, ValT>
+                                    : merge_tile_reg_kernel<RB, false, OffT, ValT>;
+            SPMV_TRY(apply_carveout(reinterpret_cast<const void *>(kernel), carveout));
+            KernelTimerScope timed(p.stream);
+            SPMV_CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, kernel, p.n_rows, p.nnz, p.Ap, p.Aj, p.Ax, p.x, p.y,
+                                             p.alpha_dev, p.peers, (const int32_t *)coords,
+                                             static_cast<int32_t *>(crow), static_cast<ValT *>(cval)));
+        }
     }
     SPMV_LAUNCH_CHECK();
 

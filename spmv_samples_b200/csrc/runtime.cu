@@ -52,6 +52,13 @@ std::map<std::string, int64_t> &options() {
         {"cusparse_preprocess", 0},  // 1: run cusparseSpMV_preprocess when a plan is built.  Only
                                      // safe while the matrix contents behind (Ap, Aj, Ax) do not
                                      // change; bench.py turns it on for the baseline timing
+        {"hot_x", -1},           // compacted hot part of x in the merge-path kernel: -1 = when the caller
+                                 // passes SPMVB200_FLAG_STATIC_PATTERN and x is longer than
+                                 // "hot_x_min_bytes"; 0 = never; 1 = always (plan keyed on the Aj pointer)
+        {"hot_x_min_bytes", 256ll << 20},
+        {"hot_x_max_bytes", 32ll << 20},   // size of the dense copy of the hot columns' x
+        {"stream_ctas_per_sm", 2},  // persistent CTAs per SM of the CSR-stream kernel
+        {"cusparse_alg", 0},     // 0: CUSPARSE_SPMV_ALG_DEFAULT (the reference's call), 1: CSR_ALG1, 2: CSR_ALG2
     };
     return o;
 }

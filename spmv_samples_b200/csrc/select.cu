@@ -75,6 +75,13 @@ void choose(spmvb200_row_stats_t &st) {
                             st.std_row_len > 1.5 * mean;
     const bool mostly_empty = st.n_rows > 0 && st.empty_rows * 2 > st.n_rows;
     st.chosen_kind = (heavy_tail || mostly_empty) ? SPMVB200_KIND_MERGE : SPMVB200_KIND_VECTOR;
+    // Short regular rows: a sub-warp per row wastes most of its 128-bit load slots (a 5-nonzero
+    // row fills 5 of 8) and every row is a chain of dependent round trips; the CSR-stream kernel
+    // moves the matrix with TMA bulk copies and gives a row to a thread.  Only worth its pipeline
+    // on a matrix large enough to fill the persistent grid a few times over.
+    if (st.chosen_kind == SPMVB200_KIND_VECTOR && st.mean_row_len <= 8.0 && st.max_row_len <= 64 &&
+        st.n_rows >= (int64_t)1 << 16)
+        st.chosen_kind = SPMVB200_KIND_STREAM;
 }
 
 }  // namespace
@@ -143,6 +150,7 @@ int launch_auto(const SpmvProblem<OffT, ValT> &p) {
     switch (st.chosen_kind) {
         case SPMVB200_KIND_VECTOR: return launch_vector<OffT, ValT>(p, st.chosen_width);
         case SPMVB200_KIND_LIGHT: return launch_light<OffT, ValT>(p, st.chosen_width);
+        case SPMVB200_KIND_STREAM: return launch_stream<OffT, ValT>(p);
         case SPMVB200_KIND_CUSPARSE: return launch_cusparse<OffT, ValT>(p);
         case SPMVB200_KIND_MERGE:
         default: return launch_merge<OffT, ValT>(p);
@@ -168,6 +176,8 @@ struct CusparsePlan {
     size_t buffer_bytes = 0;
     bool valid = false;
     bool preprocessed = false;
+    int alg = 0;
+    cudaStream_t stream = nullptr;  // the plan's work buffer belongs to one stream at a time
 };
 std::mutex g_cs_mu;
 CusparsePlan g_plan;
@@ -203,6 +213,9 @@ int launch_cusparse(const SpmvProblem<OffT, ValT> &p) {
     if (p.n_rows <= 0 || p.n_cols <= 0) return SPMVB200_OK;
     // the baseline is plain y = A*x: no device alpha, no peer fan-out
     if (p.peers.n != 0 || p.alpha_dev) return SPMVB200_ERR_UNSUPPORTED;
+    // cusparseCreateCsr rejects 64-bit offsets with 32-bit column indices: say so before any
+    // handle or descriptor exists (the reference's wrapper maps `int` only, cusparse.cuh:23-26)
+    if (sizeof(OffT) == 8) return SPMVB200_ERR_UNSUPPORTED;
     std::lock_guard<std::mutex> lk(g_cs_mu);
     int dev = -1;
     SPMV_CUDA_TRY(cudaGetDevice(&dev));
@@ -214,7 +227,14 @@ int launch_cusparse(const SpmvProblem<OffT, ValT> &p) {
     // (allocators hand the same addresses out again); it is only reused while the option
     // that asked for it is still on
     const bool want_pre = option_get("cusparse_preprocess", 0) > 0;
-    const bool hit = pl.valid && pl.preprocessed == want_pre && pl.dev == dev && pl.Ap == p.Ap && pl.Aj == p.Aj && pl.Ax == p.Ax &&
+    // "cusparse_alg": 0 = CUSPARSE_SPMV_ALG_DEFAULT (what the reference calls, cusparse.cuh:76-78),
+    // 1 = CUSPARSE_SPMV_CSR_ALG1, 2 = CUSPARSE_SPMV_CSR_ALG2
+    const int want_alg = (int)option_get("cusparse_alg", 0);
+    const cusparseSpMVAlg_t alg = want_alg == 1 ? CUSPARSE_SPMV_CSR_ALG1
+                                : want_alg == 2 ? CUSPARSE_SPMV_CSR_ALG2 : CUSPARSE_SPMV_ALG_DEFAULT;
+    // one plan = one handle + one work buffer: a call on another stream gets a fresh plan
+    // (destroying the old one frees its buffer, which waits for the work that uses it)
+    const bool hit = pl.valid && pl.preprocessed == want_pre && pl.alg == want_alg && pl.stream == p.stream && pl.dev == dev && pl.Ap == p.Ap && pl.Aj == p.Aj && pl.Ax == p.Ax &&
                      pl.n_rows == p.n_rows && pl.n_cols == p.n_cols && pl.nnz == (int64_t)p.nnz &&
                      pl.off_bits == (int)sizeof(OffT) * 8 && pl.val_bits == (int)sizeof(ValT) * 8;
     if (!hit) {
@@ -223,6 +243,8 @@ int launch_cusparse(const SpmvProblem<OffT, ValT> &p) {
         pl.Ap = p.Ap; pl.Aj = p.Aj; pl.Ax = p.Ax;
         pl.n_rows = p.n_rows; pl.n_cols = p.n_cols; pl.nnz = (int64_t)p.nnz;
         pl.off_bits = (int)sizeof(OffT) * 8; pl.val_bits = (int)sizeof(ValT) * 8;
+        pl.alg = want_alg;
+        pl.stream = p.stream;
         SPMV_CUSPARSE_TRY(cusparseCreate(&pl.handle));
         SPMV_CUSPARSE_TRY(cusparseCreateCsr(&pl.mat, p.n_rows, p.n_cols, (int64_t)p.nnz,
                                             const_cast<OffT *>(p.Ap), const_cast<int32_t *>(p.Aj),
@@ -233,20 +255,20 @@ int launch_cusparse(const SpmvProblem<OffT, ValT> &p) {
         SPMV_CUSPARSE_TRY(cusparseSetStream(pl.handle, p.stream));
         SPMV_CUSPARSE_TRY(cusparseSpMV_bufferSize(pl.handle, CUSPARSE_OPERATION_NON_TRANSPOSE, &one,
                                                   pl.mat, pl.vx, &zero, pl.vy, vt,
-                                                  CUSPARSE_SPMV_ALG_DEFAULT, &pl.buffer_bytes));
+                                                  alg, &pl.buffer_bytes));
         SPMV_CUDA_TRY(cudaMalloc(&pl.buffer, pl.buffer_bytes ? pl.buffer_bytes : 16));
         pl.preprocessed = option_get("cusparse_preprocess", 0) > 0;
         if (pl.preprocessed)
             SPMV_CUSPARSE_TRY(cusparseSpMV_preprocess(pl.handle, CUSPARSE_OPERATION_NON_TRANSPOSE,
                                                       &one, pl.mat, pl.vx, &zero, pl.vy, vt,
-                                                      CUSPARSE_SPMV_ALG_DEFAULT, pl.buffer));
+                                                      alg, pl.buffer));
         pl.valid = true;
     }
     SPMV_CUSPARSE_TRY(cusparseSetStream(pl.handle, p.stream));
     SPMV_CUSPARSE_TRY(cusparseDnVecSetValues(pl.vx, const_cast<ValT *>(p.x)));
     SPMV_CUSPARSE_TRY(cusparseDnVecSetValues(pl.vy, p.y));
     SPMV_CUSPARSE_TRY(cusparseSpMV(pl.handle, CUSPARSE_OPERATION_NON_TRANSPOSE, &one, pl.mat, pl.vx,
-                                   &zero, pl.vy, vt, CUSPARSE_SPMV_ALG_DEFAULT, pl.buffer));
+                                   &zero, pl.vy, vt, alg, pl.buffer));
     return SPMVB200_OK;
 }
 template int launch_cusparse<int32_t, float>(const SpmvProblem<int32_t, float> &);

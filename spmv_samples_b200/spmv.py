@@ -78,6 +78,12 @@ def SpMV_light(n_rows, n_cols, nnz, Ap, Aj, Ax, x, y, stream=None):
     _typed_call("light", n_rows, n_cols, nnz, Ap, Aj, Ax, x, y, stream)
 
 
+def SpMV_stream(n_rows, n_cols, nnz, Ap, Aj, Ax, x, y, stream=None):
+    """CSR-stream kernel: TMA-staged row tiles, thread per row (short regular rows; the
+    THREADS_PER_VECTOR = 2 / 4 case of cusp/cusp.cuh:189-203)."""
+    _typed_call("stream", n_rows, n_cols, nnz, Ap, Aj, Ax, x, y, stream)
+
+
 def SpMV_auto(n_rows, n_cols, nnz, Ap, Aj, Ax, x, y, stream=None):
     """Host selector: row statistics -> one of the kernels above."""
     _typed_call("auto", n_rows, n_cols, nnz, Ap, Aj, Ax, x, y, stream)
@@ -93,11 +99,22 @@ SPMV_KINDS = {
     "merge": SpMV_merge,
     "vector": SpMV_vector,
     "light": SpMV_light,
+    "stream": SpMV_stream,
     "auto": SpMV_auto,
     "cusparse": SpMV_cusparse,
+    # the reference's own labels (spmv.h:18-27), each served by the kernel that replaces it
+    "cusp": SpMV_vector,
+    "cusp1": SpMV_vector,
+    "cusp2": SpMV_vector,
+    "light_vec": SpMV_light,
+    "light_warp": SpMV_light,
+    "cub_merge": SpMV_merge,
 }
+REFERENCE_ALIASES = {"cusp": "vector", "cusp1": "vector", "cusp2": "vector", "light_vec": "light",
+                     "light_warp": "light", "cub_merge": "merge"}
 KIND_IDS = {"merge": _lib.KIND_MERGE, "vector": _lib.KIND_VECTOR, "light": _lib.KIND_LIGHT,
-            "auto": _lib.KIND_AUTO, "cusparse": _lib.KIND_CUSPARSE}
+            "stream": _lib.KIND_STREAM, "auto": _lib.KIND_AUTO, "cusparse": _lib.KIND_CUSPARSE}
+KIND_IDS.update({alias: KIND_IDS[target] for alias, target in REFERENCE_ALIASES.items()})
 
 
 def SpMV(kind_str, n_rows, n_cols, nnz, Ap, Aj, Ax, x, y, stream=None):
@@ -277,3 +294,17 @@ def get_option(name: str) -> int:
 
 def launch_count() -> int:
     return int(_lib.lib().spmvb200_launch_count())
+
+
+def hot_x_info(Aj) -> dict:
+    """What the merge-path kernel's hot-x plan holds for this Aj on its device (csrc/hotx.cu):
+    hot_columns = 0 when no plan exists."""
+    k, share, ms = C.c_int64(0), C.c_double(0.0), C.c_double(0.0)
+    with torch.cuda.device(Aj.device):
+        st = _lib.lib().spmvb200_hot_x_info(_ptr(Aj), C.byref(k), C.byref(share), C.byref(ms))
+    _lib.check(st, "spmvb200_hot_x_info")
+    return {"hot_columns": int(k.value), "hot_share": float(share.value), "build_ms": float(ms.value)}
+
+
+def release_cache() -> None:
+    _lib.lib().spmvb200_release_cache()

@@ -50,7 +50,15 @@ def test_status_strings_and_options(built_lib):
 
 def test_python_mirror_has_reference_surface():
     from spmv_samples_b200 import spmv
-    assert set(spmv.SPMV_KINDS) == {"merge", "vector", "light", "auto", "cusparse"}
+    ours = {"merge", "vector", "light", "stream", "auto", "cusparse"}
+    # every label of the reference's table (spmv.h:18-27) is accepted; "merge_genl" lives behind
+    # spmv_ex(semiring=...) in the Python mirror and is an X line of include/spmv.h
+    reference = {"cusparse", "cusp", "cusp1", "cusp2", "light_vec", "light_warp", "cub_merge", "merge"}
+    assert set(spmv.SPMV_KINDS) == ours | reference
+    assert set(spmv.KIND_IDS) == set(spmv.SPMV_KINDS)
+    hdr = open(os.path.join(ROOT, "include", "spmv.h")).read()
+    for label in ours | reference | {"merge_genl"}:
+        assert f'X("{label}",' in hdr, label
     import inspect
     params = list(inspect.signature(spmv.SpMV).parameters)
     assert params[:9] == ["kind_str", "n_rows", "n_cols", "nnz", "Ap", "Aj", "Ax", "x", "y"]

@@ -20,7 +20,7 @@ from oracle import cpu
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
-OURS = ["merge", "vector", "light", "auto"]
+OURS = ["merge", "vector", "light", "stream", "auto"]
 TOL = {torch.float32: 1e-5, torch.float64: 1e-13}
 
 

@@ -229,3 +229,34 @@ def test_errors_come_from_one_place_whatever_the_size(shim, tmp_path, monkeypatc
             f.write(f"{1 + i % 1000} {1 + (7 * i) % 1000} 1.5\n")
     rc, msg = load(shim, path)
     assert rc == 100 and "Could not read weighted edge" in msg
+
+
+@pytest.mark.parametrize("threads", ["1", "4"])
+def test_out_of_range_indices_are_rejected(shim, tmp_path, monkeypatch, threads):
+    """An index beyond the header's dimensions is an error in every parse path (the reference
+    stores it unchecked, load.hpp:330-331, and its ToCsr then indexes past row_offsets)."""
+    monkeypatch.setenv("SPMV_LOADER_THREADS", threads)
+    p = str(tmp_path / "oob.mtx")
+    open(p, "w").write("%%MatrixMarket matrix coordinate real general\n3 3 3\n1 1 1.0\n2 7 2.0\n3 3 3.0\n")
+    rc, msg = load(shim, p)
+    assert rc == 100 and "column index exceeds" in msg
+    open(p, "w").write("%%MatrixMarket matrix coordinate pattern symmetric\n3 3 2\n1 1\n4 2\n")
+    rc, msg = load(shim, p)
+    assert rc == 100 and "row index exceeds" in msg
+    # deep inside a file large enough for the threaded by-line path and the threaded ToCsr
+    with open(p, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real general\n1000 1000 200000\n")
+        for i in range(200000):
+            f.write(f"{1001 if i == 123456 else 1 + i % 1000} {1 + (7 * i) % 1000} 1.5\n")
+    rc, msg = load(shim, p)
+    assert rc == 100 and "row index exceeds" in msg
+    with open(p, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real general\n1000 1000 200000\n")
+        for i in range(200000):
+            f.write(f"{1 + i % 1000} {1001 if i == 199999 else 1 + (7 * i) % 1000} 1.5\n")
+    rc, msg = load(shim, p)
+    assert rc == 100 and "column index exceeds" in msg
+    # the largest legal indices still load
+    open(p, "w").write("%%MatrixMarket matrix coordinate real general\n3 4 1\n3 4 2.5\n")
+    rc, out = load(shim, p)
+    assert rc == 0 and out[2].tolist() == [0, 0, 0, 1] and out[3].tolist() == [3]

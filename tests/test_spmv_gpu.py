@@ -15,8 +15,8 @@ from oracle import cpu, generators as g
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
-KINDS = ["merge", "vector", "light", "auto", "cusparse"]
-OURS = ["merge", "vector", "light", "auto"]
+KINDS = ["merge", "vector", "light", "stream", "auto", "cusparse"]
+OURS = ["merge", "vector", "light", "stream", "auto"]
 TOL = {np.dtype(np.float32): 1e-5, np.dtype(np.float64): 1e-13}
 
 
@@ -178,16 +178,32 @@ def test_edge_cases(case, kind):
 
 
 @pytest.mark.parametrize("kind", OURS)
-def test_zero_rows_is_a_noop(kind):
+def test_zero_rows_is_a_noop_and_zero_cols_gives_zero(kind):
     from spmv_samples_b200 import spmv
     Ap = torch.zeros(1, dtype=torch.int32, device="cuda")
     e_i = torch.zeros(4, dtype=torch.int32, device="cuda")
     e_f = torch.zeros(4, dtype=torch.float32, device="cuda")
     y = torch.full((4,), 7.0, device="cuda")
-    spmv.SpMV(kind, 0, 4, 0, Ap, e_i, e_f, e_f, y)      # n_rows == 0
+    spmv.SpMV(kind, 0, 4, 0, Ap, e_i, e_f, e_f, y)      # n_rows == 0: nothing to write
+    torch.cuda.synchronize()
+    assert torch.all(y == 7.0)
+    # n_cols == 0: every row is empty, so y = 0 as the reference's CPU loop gives
+    # (cpu_navie.hpp:9-16); its merge kind returns early and leaves y stale
+    # (dispatch_spmv_orig.cuh:564-570) -- "y is fully overwritten" wins here
     spmv.SpMV(kind, 4, 0, 0, torch.zeros(5, dtype=torch.int32, device="cuda"), e_i, e_f, e_f, y)
     torch.cuda.synchronize()
-    assert torch.all(y == 7.0)   # dispatch_spmv_orig.cuh:564-570: nothing is written
+    assert torch.all(y == 0.0)
+
+
+def test_zero_cols_with_nonzeros_is_invalid():
+    from spmv_samples_b200 import spmv, _lib
+    Ap = torch.tensor([0, 1, 2], dtype=torch.int32, device="cuda")
+    e_i = torch.zeros(4, dtype=torch.int32, device="cuda")
+    e_f = torch.zeros(4, dtype=torch.float32, device="cuda")
+    y = torch.zeros(2, device="cuda")
+    with pytest.raises(_lib.SpmvB200Error) as ei:
+        spmv.SpMV("merge", 2, 0, 2, Ap, e_i, e_f, e_f, y)
+    assert ei.value.status == 1      # SPMVB200_ERR_INVALID
 
 
 def test_misaligned_pointer_is_rejected():
@@ -298,7 +314,7 @@ def test_device_coo_to_csr_with_values_matches_oracle():
 
 
 # ------------------------------------------------------------------ alpha, peers, host API
-@pytest.mark.parametrize("kind", ["merge", "vector", "light"])
+@pytest.mark.parametrize("kind", ["merge", "vector", "light", "stream"])
 def test_device_alpha_and_peer_replicas(kind):
     from spmv_samples_b200 import spmv
     Ap, Aj, Ax = g.ragged(6000, 1500, 8.0, 6, heavy_len=9000)
@@ -580,3 +596,138 @@ def test_light_tiers(case, off, val):
         spmv.set_option("light_rows_per_claim", 0)
     assert_within_tolerance(y1, Ap, Aj, Ax, x, f"light tiers {case}")
     assert np.array_equal(y1, y2)
+
+
+# ------------------------------------------------------------------ CSR-stream specifics
+@pytest.mark.parametrize("off", [np.int32, np.int64])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("case", ["lap2d", "short_ragged", "one_long_row", "chunked_tiles", "tail_not_mult_of_4"])
+def test_stream_kernel_shapes(case, dtype, off):
+    """Tiles of 256 rows staged by TMA: partial last tile, tiles that need several 2048-nonzero
+    chunks, rows spanning chunks, nnz not a multiple of 4 (the plain-load tail), empty tiles."""
+    if case == "lap2d":
+        Ap, Aj, Ax = g.lap2d(97, dtype=dtype, offset_dtype=off)           # 9409 rows: partial tile
+    elif case == "short_ragged":
+        Ap, Aj, Ax = _csr(np.random.default_rng(1).integers(0, 9, 70001), 5000, 3, dtype, off)
+    elif case == "one_long_row":
+        lens = np.full(1000, 3); lens[517] = 30000                        # 15 chunks inside one tile
+        Ap, Aj, Ax = _csr(lens, 4000, 4, dtype, off)
+    elif case == "chunked_tiles":
+        Ap, Aj, Ax = _csr(np.random.default_rng(2).integers(20, 60, 3000), 2500, 5, dtype, off)
+    else:
+        lens = np.zeros(1300, dtype=np.int64); lens[:1021] = 1; lens[1299] = 2   # nnz = 1023, empty tiles
+        Ap, Aj, Ax = _csr(lens, 64, 6, dtype, off)
+    x = g.gen_x(11, int(Aj.max()) + 1 if Aj.size else 8, dtype)
+    y = run_kind("stream", Ap, Aj, Ax, x)
+    assert_within_tolerance(y, Ap, Aj, Ax, x, f"stream/{case}")
+
+
+def test_stream_sums_in_row_order():
+    """One thread per row adds the products in CSR order, like the reference's CPU loop
+    (cpu_navie.hpp:9-16): the result does not depend on the launch geometry."""
+    from spmv_samples_b200 import spmv
+    Ap, Aj, Ax = _csr(np.random.default_rng(3).integers(0, 12, 20000), 3000, 7)
+    x = g.gen_x(12, 3000)
+    y2 = run_kind("stream", Ap, Aj, Ax, x)
+    spmv.set_option("stream_ctas_per_sm", 1)
+    try:
+        y1 = run_kind("stream", Ap, Aj, Ax, x)
+    finally:
+        spmv.set_option("stream_ctas_per_sm", 2)
+    assert np.array_equal(y1, y2)
+
+
+def test_reference_labels_are_aliases():
+    """reference/include/spmv.h:18-27: every label of the reference's table runs."""
+    Ap, Aj, Ax = g.uniform_rows(2000, 2000, 16, 9)
+    x = g.gen_x(13, 2000)
+    for alias, target in (("cusp", "vector"), ("cusp1", "vector"), ("cusp2", "vector"),
+                          ("light_vec", "light"), ("light_warp", "light"), ("cub_merge", "merge")):
+        assert np.array_equal(run_kind(alias, Ap, Aj, Ax, x), run_kind(target, Ap, Aj, Ax, x))
+
+
+# ------------------------------------------------------------------ hot-x plan (csrc/hotx.cu)
+@pytest.mark.parametrize("off", [np.int32, np.int64])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_hot_x_plan_is_bit_identical(dtype, off):
+    """The remapped Aj + dense x_hot change where x is read from, not what is added or in which
+    order: y must be bit-identical to the plain merge kernel's, and within tolerance of the oracle."""
+    from spmv_samples_b200 import spmv
+    Ap, Aj, Ax = g.rmat(15, 16, 21, dtype=dtype, offset_dtype=off)
+    x = g.gen_x(5, 1 << 15, dtype)
+    dAp, dAj, dAx, dx = dev(Ap), dev(Aj), dev(Ax), dev(x)
+    y0 = torch.full((1 << 15,), float("nan"), dtype=dAx.dtype, device="cuda")
+    y1 = torch.full_like(y0, float("nan"))
+    spmv.release_cache()
+    spmv.SpMV("merge", 1 << 15, 1 << 15, Aj.size, dAp, dAj, dAx, dx, y0)
+    spmv.set_option("hot_x", 1)
+    spmv.set_option("hot_x_max_bytes", 4096 * x.itemsize)     # 4096 hot columns
+    try:
+        spmv.SpMV("merge", 1 << 15, 1 << 15, Aj.size, dAp, dAj, dAx, dx, y1)
+        torch.cuda.synchronize()
+        info = spmv.hot_x_info(dAj)
+        # a new x through the same plan: x_hot is refilled on every call
+        x2 = g.gen_x(6, 1 << 15, dtype)
+        y2 = torch.full_like(y0, float("nan"))
+        spmv.SpMV("merge", 1 << 15, 1 << 15, Aj.size, dAp, dAj, dAx, dev(x2), y2)
+        torch.cuda.synchronize()
+    finally:
+        spmv.set_option("hot_x", -1)
+        spmv.set_option("hot_x_max_bytes", 32 << 20)
+        spmv.release_cache()
+    assert 0 < info["hot_columns"] <= 4096 and 0.25 <= info["hot_share"] <= 1.0
+    assert np.array_equal(y0.cpu().numpy(), y1.cpu().numpy())
+    assert_within_tolerance(y1.cpu().numpy(), Ap, Aj, Ax, x, "merge + hot_x")
+    assert_within_tolerance(y2.cpu().numpy(), Ap, Aj, Ax, x2, "merge + hot_x, second x")
+    # the hot set is the set of most frequent columns
+    cnt = np.bincount(Aj, minlength=1 << 15)
+    thr = np.sort(cnt)[::-1][info["hot_columns"] - 1]
+    assert abs(info["hot_share"] - cnt[cnt >= thr].sum() / Aj.size) < 1e-12
+
+
+def test_hot_x_plan_declines_a_flat_column_distribution():
+    """Uniform columns: no hot set takes 25 % of the gathers, so no plan (and no second Aj)."""
+    from spmv_samples_b200 import spmv
+    Ap, Aj, Ax = g.uniform_rows(20000, 20000, 16, 3)
+    x = g.gen_x(7, 20000)
+    spmv.release_cache()
+    spmv.set_option("hot_x", 1)
+    spmv.set_option("hot_x_max_bytes", 4 * 1000)
+    try:
+        dAj = dev(Aj)
+        y = torch.full((20000,), float("nan"), device="cuda")
+        spmv.SpMV("merge", 20000, 20000, Aj.size, dev(Ap), dAj, dev(Ax), dev(x), y)
+        torch.cuda.synchronize()
+        info = spmv.hot_x_info(dAj)
+    finally:
+        spmv.set_option("hot_x", -1)
+        spmv.set_option("hot_x_max_bytes", 32 << 20)
+        spmv.release_cache()
+    assert info["hot_columns"] == 0
+    assert_within_tolerance(y.cpu().numpy(), Ap, Aj, Ax, x, "merge, hot_x declined")
+
+
+def test_hot_x_plan_through_the_static_pattern_flag_and_peers():
+    """Default policy: a plan is built only for a caller that passes STATIC_PATTERN and an x beyond
+    hot_x_min_bytes; it also serves the peer fan-out kernel."""
+    from spmv_samples_b200 import spmv
+    Ap, Aj, Ax = g.rmat(14, 16, 5)
+    n = 1 << 14
+    x = g.gen_x(8, n)
+    dAp, dAj, dAx, dx = dev(Ap), dev(Aj), dev(Ax), dev(x)
+    spmv.release_cache()
+    spmv.set_option("hot_x_min_bytes", 1024)
+    try:
+        y = torch.full((n,), float("nan"), device="cuda")
+        spmv.spmv_ex("merge", dAp, dAj, dAx, dx, y)                      # no flag: no plan
+        torch.cuda.synchronize()
+        assert spmv.hot_x_info(dAj)["hot_columns"] == 0
+        ref = y.clone()
+        rep = torch.zeros(n, device="cuda")
+        spmv.spmv_ex("merge", dAp, dAj, dAx, dx, y, static_pattern=True, y_peers=[rep.data_ptr()])
+        torch.cuda.synchronize()
+        assert spmv.hot_x_info(dAj)["hot_columns"] > 0
+        assert torch.equal(y, ref) and torch.equal(rep, ref)
+    finally:
+        spmv.set_option("hot_x_min_bytes", 256 << 20)
+        spmv.release_cache()

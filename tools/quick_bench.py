@@ -76,5 +76,9 @@ for cfg in a.configs.split(","):
                   f"{m.flops()/t/1e9:8.1f} GFLOP/s  (min {ts[0]*1e6:.1f} us)", flush=True)
         except Exception as e:
             print(f"   {kind:9s} FAILED: {e}", flush=True)
+    hx = spmv.hot_x_info(m.Aj)
+    if hx["hot_columns"]:
+        print(f"   hot-x plan: {hx['hot_columns']} columns, {100*hx['hot_share']:.1f}% of the gathers, built in {hx['build_ms']:.1f} ms", flush=True)
+    spmv.release_cache()
     del m, x, y
     torch.cuda.empty_cache()
