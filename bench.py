@@ -65,6 +65,8 @@ def parse_args():
     p.add_argument("--cpu-seconds", type=float, default=15.0,
                    help="budget of the cpu_baseline leg (own arm)")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-configs", action="store_true",
+                   help="skip the c1..c4 + cuSPARSE leg (N = 1 only; outside the timed region)")
     return p.parse_args()
 
 
@@ -74,6 +76,37 @@ def measured_peak():
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def kernel_source_sha():
+    """sha1 over the sources of the dominant kernels: a traffic figure captured under ncu is only
+    quoted while the kernel it was captured from is the kernel that ran."""
+    import hashlib
+    h = hashlib.sha1()
+    for f in ("merge.cu", "hotx.cu", "common.cuh", "vector.cu", "stream.cu", "light.cu", "row_dot.cuh"):
+        try:
+            h.update(open(os.path.join(ROOT, "spmv_samples_b200", "csrc", f), "rb").read())
+        except OSError:
+            pass
+    return h.hexdigest()[:16]
+
+
+def traffic_lookup(workload_key, kernel):
+    """DRAM bytes per launch of `kernel` on `workload_key` from profiles/traffic.json (one
+    `ncu --set full` capture each), or None when the capture belongs to another kernel or to
+    an older version of the kernel sources."""
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return None, "profiles/traffic.json missing"
+    sha = kernel_source_sha()
+    for e in tj.get("captures", []):
+        if e.get("workload") == workload_key and e.get("kernel") == kernel:
+            if e.get("kernel_source_sha") == sha:
+                return e.get("dram_bytes"), e.get("source")
+            return None, (f"capture of {kernel} exists ({e.get('source')}) but predates the current "
+                          f"kernel sources (sha {e.get('kernel_source_sha')} vs {sha}): not quoted")
+    return None, f"no capture of {kernel} on {workload_key}"
 
 
 def workload_desc(name, override):
@@ -231,6 +264,150 @@ def cpu_reference_leg(global_csr, x_dev, steps, warmup, seconds_budget, sample_n
     return 2.0 * nnz_s / dt / 1e9, info
 
 
+# --------------------------------------------------------------------------- parity leg
+TOL = {4: 1e-5, 8: 1e-13}   # |y - y_ref| <= tol * sum_j |a_ij x_j| per row (BASELINE.json north_star)
+
+
+def parity_leg(csr, x, y, n_random=3000, n_heavy=6, seed=0):
+    """Checker, outside every timed region: y (device, one plain SpMV of `csr`) against the fp64
+    oracle on a row sample -- the `n_heavy` longest rows, `n_random` random rows, the first and the
+    last -- gathered into a sub-CSR on the device and evaluated on the host by oracle.cpu
+    (the restatement of reference/include/spmv/cpu_navie.hpp:3-35, pinned to oracle/_ref)."""
+    import numpy as np
+    import torch
+
+    from oracle import cpu
+
+    if csr.n_rows == 0:
+        return {"rows_sampled": 0, "max_err_over_scale": 0.0, "tol": None, "ok": True}
+    lens = csr.Ap[1:] - csr.Ap[:-1]
+    heavy = torch.topk(lens, min(n_heavy, csr.n_rows)).indices
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    rnd = torch.randint(0, csr.n_rows, (n_random,), device="cuda", generator=gen)
+    rows = torch.unique(torch.cat([heavy, rnd, torch.tensor([0, csr.n_rows - 1], device="cuda")]))
+    starts, ends = csr.Ap[rows].long(), csr.Ap[rows + 1].long()
+    seg = ends - starts
+    sub_Ap = torch.zeros(rows.numel() + 1, dtype=torch.int64, device="cuda")
+    sub_Ap[1:] = torch.cumsum(seg, 0)
+    total = int(sub_Ap[-1])
+    pos = torch.arange(total, device="cuda") - torch.repeat_interleave(sub_Ap[:-1], seg) \
+        + torch.repeat_interleave(starts, seg)
+    Aj, Ax, Ap = csr.Aj[pos].cpu().numpy(), csr.Ax[pos].cpu().numpy(), sub_Ap.cpu().numpy()
+    xh = x.cpu().numpy()
+    y64 = cpu.spmv_fp64(Ap, Aj, Ax, xh)
+    scale = cpu.abs_scale(Ap, Aj, Ax, xh)
+    got = y[rows].cpu().numpy().astype(np.float64)
+    tol = TOL[csr.Ax.element_size()]
+    err = np.abs(got - y64)
+    nz = scale > 0
+    ratio = float((err[nz] / scale[nz]).max()) if nz.any() else 0.0
+    ok = bool(np.all(err <= tol * scale))
+    return {"rows_sampled": int(rows.numel()), "nnz_sampled": total, "max_err_over_scale": ratio,
+            "tol": tol, "ok": ok,
+            "oracle": "oracle.cpu.spmv_fp64 (fp64 restatement of cpu_navie.hpp:3-17) on the "
+                      f"{n_heavy} longest rows + {n_random} random rows + first + last"}
+
+
+# --------------------------------------------------------------------------- configs leg
+def _median_us(fn, flush, iters):
+    import torch
+    ts = []
+    for _ in range(iters):
+        flush.zero_()            # L2 flushed: 512 MB written between timed calls
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def configs_leg(peak, iters=15):
+    """c1..c4 of BASELINE.json at full size, one GPU: every kind of this library and cuSPARSE
+    (setup hoisted; ALG_DEFAULT as the reference calls it, cusparse.cuh:76-78, then with
+    cusparseSpMV_preprocess, then CSR_ALG2), CUDA events around single calls with the L2 flushed in
+    between, median; the selector's choice; a same-size device copy and the pure-gather yardstick;
+    parity of the selected kernel on sampled rows.  Outside the timed region of the headline."""
+    import torch
+
+    from spmv_samples_b200 import generate, spmv
+    kind_names = {0: "merge", 1: "vector", 2: "light", 3: "auto", 4: "cusparse", 5: "stream"}
+    spmv.set_option("time_main_kernel", 0)   # the per-kernel event pair costs ~5 us per call: headline leg only
+    flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
+    out = {}
+    yard = {}
+    for cfg in ("c1", "c2", "c3", "c4"):
+        m = generate.make_config(cfg, SEED)
+        x = generate.gen_x(m.n_cols, SEED, m.Ax.dtype)
+        y = torch.empty(m.n_rows, dtype=m.Ax.dtype, device="cuda")
+        st = spmv.row_stats(m.Ap, nnz=m.nnz)
+        alg = m.algorithmic_bytes()
+        call = lambda k: spmv.SpMV(k, m.n_rows, m.n_cols, m.nnz, m.Ap, m.Aj, m.Ax, x, y)
+        ours = {}
+        # "stream" gives a row to a thread: only timed on the matrices it is meant for (a hub row
+        # of R-MAT scale 24 keeps one thread busy for a second)
+        kinds = ["merge", "vector", "light", "auto"]
+        if st["mean_row_len"] <= 8.0 and st["max_row_len"] <= 64:
+            kinds.insert(3, "stream")
+        for k in kinds:
+            for _ in range(3):
+                call(k)
+            ours[k] = round(_median_us(lambda: call(k), flush, iters), 2)
+        best = min((k for k in kinds if k != "auto"), key=lambda k: ours[k])
+        call("auto")
+        torch.cuda.synchronize()
+        par = parity_leg(m, x, y)
+        cus = {}
+        for label, opts in (("alg_default", {"cusparse_alg": 0, "cusparse_preprocess": 0}),
+                            ("alg_default_preprocess", {"cusparse_alg": 0, "cusparse_preprocess": 1}),
+                            ("csr_alg2", {"cusparse_alg": 2, "cusparse_preprocess": 0})):
+            try:
+                for name, v in opts.items():
+                    spmv.set_option(name, v)
+                for _ in range(3):
+                    call("cusparse")
+                cus[label] = round(_median_us(lambda: call("cusparse"), flush, iters), 2)
+            except Exception as e:   # the baseline is reported, never required
+                cus[label] = None
+                cus[label + "_error"] = str(e)[:120]
+        spmv.set_option("cusparse_alg", 0)
+        spmv.set_option("cusparse_preprocess", 0)
+        half = alg // 8
+        src = torch.empty(half, dtype=torch.float32, device="cuda")
+        dst = torch.empty_like(src)
+        copy_us = _median_us(lambda: dst.copy_(src), flush, iters)
+        del src, dst
+        t_auto = ours["auto"] * 1e-6
+        entry = {
+            "desc": generate.CONFIGS[cfg]["desc"], "rows": m.n_rows, "nnz": m.nnz,
+            "algorithmic_bytes": alg, "selected_kernel": kind_names.get(st["chosen_kind"]),
+            "us": ours, "best_kind": best,
+            "auto_gbs": alg / t_auto / 1e9, "auto_gflops": m.flops() / t_auto / 1e9,
+            "frac": alg / t_auto / 1e9 / peak, "frac_of_datasheet_8000": alg / t_auto / 1e9 / 8000.0,
+            "cusparse_us": cus, "copy_same_bytes_us": round(copy_us, 2),
+            "parity": par,
+        }
+        best_cus = min([v for k, v in cus.items() if isinstance(v, float)], default=None)
+        entry["auto_over_best_cusparse"] = (best_cus / ours["auto"]) if best_cus else None
+        if cfg in ("c2", "c3"):
+            key = m.n_cols
+            if key not in yard:
+                yard[key] = spmv.gather_yardstick(m.n_cols)
+            entry["gather_yardstick_ggathers_s"] = yard[key]
+            entry["auto_ggathers_s"] = m.nnz / t_auto / 1e9
+        out[cfg] = entry
+        spmv.release_cache()
+        del m, x, y
+        torch.cuda.empty_cache()
+    out["_method"] = ("CUDA events around one call, L2 flushed (512 MB written) before each, median of "
+                      f"{iters}; cuSPARSE handle / descriptors / buffer created once outside the timing")
+    del flush
+    torch.cuda.empty_cache()
+    return out
+
+
 # --------------------------------------------------------------------------- reference arm
 def reference_arm(args, rank, world):
     if rank != 0:
@@ -375,12 +552,42 @@ def own_arm(args, rank, world, local_rank):
     # ---- roofline of the dominant kernel on rank 0's shard
     alg_bytes_local = local.algorithmic_bytes()
     achieved = alg_bytes_local / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
-    traffic = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tj.get(f"{args.workload}@{world}")
-    except Exception:
-        pass
+    hot = spmv.hot_x_info(local.Aj)
+    main_kernel = ("merge_tile_hot_kernel" if hot["hot_columns"] else "merge_tile_reg_kernel") \
+        if stats["chosen_kind"] == 0 else {1: "vector_kernel", 2: "light_kernel", 5: "stream_kernel"}.get(
+            stats["chosen_kind"], "?")
+    traffic, traffic_note = traffic_lookup(f"{args.workload}@{world}", main_kernel)
+
+    # ---- parity, outside the timed region: one plain SpMV of this rank's row block against the
+    # fp64 oracle on sampled rows; then the x replicas of all ranks bit for bit (what the fused
+    # exchange -- peer stores or multicast -- wrote must be the same vector everywhere)
+    x_now = it.current_x()
+    y_chk = torch.full((local.n_rows,), float("nan"), dtype=local.Ax.dtype, device="cuda")
+    spmv.spmv_ex(args.kind, local.Ap, local.Aj, local.Ax, x_now, y_chk, n_cols=n_cols)
+    torch.cuda.synchronize()
+    par = parity_leg(local, x_now, y_chk, seed=rank)
+    del y_chk
+    par_all = torch.tensor([[1.0 if par["ok"] else 0.0, par["max_err_over_scale"], par["rows_sampled"], 1.0]],
+                           dtype=torch.float64, device="cuda").repeat(world, 1)
+    if world > 1:
+        ref = x_now.clone()
+        dist.broadcast(ref, src=0)
+        par_all[:, 3] = 1.0 if torch.equal(ref.view(torch.int32), x_now.view(torch.int32)) else 0.0
+        del ref
+        gathered = [torch.zeros_like(par_all[0]) for _ in range(world)]
+        dist.all_gather(gathered, par_all[rank].contiguous())
+        par_all = torch.stack(gathered)
+    par_all = par_all.cpu().tolist()
+    parity = {
+        "ok": all(r[0] == 1.0 for r in par_all) and all(r[3] == 1.0 for r in par_all),
+        "max_err_over_scale": max(r[1] for r in par_all), "tol": par["tol"],
+        "rows_sampled": int(sum(r[2] for r in par_all)),
+        "per_rank_ok": [r[0] == 1.0 for r in par_all],
+        "x_replicas_bit_identical": all(r[3] == 1.0 for r in par_all) if world > 1 else None,
+        "what": "one plain SpMV of every rank's row block vs " + par.get("oracle", "the fp64 oracle")
+                + ("; then every rank's replica of x after the timed steps compared bit for bit with rank 0's"
+                   if world > 1 else ""),
+    }
 
     # ---- e2e: the host-buffer API, x H2D + kernel + y D2H every step, pinned host memory
     e2e = None
@@ -431,10 +638,10 @@ def own_arm(args, rank, world, local_rank):
         # all-gathered over NVLink, every rank downloads its slice of y
         from spmv_samples_b200.dist import ShardedHostSpMV
         hs = ShardedHostSpMV(shard, n, kind=args.kind, slots=ns)
-        rows_local = local.n_rows
+        rows_local = hs.io_end - hs.io_begin
         xs = [torch.empty(rows_local, dtype=local.Ax.dtype, pin_memory=True) for _ in range(ns)]
         ys = [torch.empty(rows_local, dtype=local.Ax.dtype, pin_memory=True) for _ in range(ns)]
-        xs[0].copy_(it.current_x()[shard.row_begin:shard.row_end].cpu())
+        xs[0].copy_(it.current_x()[hs.io_begin:hs.io_end].cpu())
         for t in xs[1:]:
             t.copy_(xs[0])
         hs.spmv_many([xs[i % ns] for i in range(ns)], [ys[i % ns] for i in range(ns)])
@@ -444,45 +651,69 @@ def own_arm(args, rank, world, local_rank):
                "d2h_bytes_per_step": int(n * ys[0].element_size()),
                "steps": k, "ms_per_step": dt / k * 1e3,
                "api": "spmv_samples_b200.dist.ShardedHostSpMV.spmv_many: matrix resident and "
-                      "row-sharded; every step each rank uploads its slice of x from pinned host "
-                      "memory, the slices are all-gathered over NVLink (NCCL), the SpMV runs, each rank "
-                      f"downloads its slice of y; bytes are totals over the ranks; {ns} steps in flight"}
+                      "row-sharded (nnz-balanced); host I/O in even slices: every step each rank uploads "
+                      "n/N values of x from pinned host memory, the slices are all-gathered over NVLink "
+                      "(NCCL), the SpMV runs, the computed rows go to the ranks whose host slice they "
+                      "belong to (one all-to-all, uneven splits) and each rank downloads n/N values of y; "
+                      f"bytes are totals over the ranks; {ns} steps in flight"}
         hs.close()
 
+    exchange_used, exchange_note = it.exchange, getattr(it, "exchange_note", "")
+    offset_bits = local.Ap.element_size() * 8
+    value_dtype = "f32" if local.Ax.dtype == torch.float32 else "f64"
     it.close()
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        del it, shard, local
+        try:
+            del gm
+        except NameError:
+            pass
+        spmv.release_cache()
+        torch.cuda.empty_cache()
+        try:
+            configs = configs_leg(peak)
+        except Exception as e:
+            configs = {"error": str(e)[:300]}
     if rank == 0:
-        kind_names = {0: "merge", 1: "vector", 2: "light", 3: "auto", 4: "cusparse"}
+        kind_names = {0: "merge", 1: "vector", 2: "light", 3: "auto", 4: "cusparse", 5: "stream"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32"
-            if local.Ax.dtype == torch.float32 else "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": value_dtype,
+            "data": "synthetic",
             "gbs": gbs, "roofline_frac_step": gbs / peak / world,
             "config": {
                 "workload": workload_desc(args.workload, args.override), "seed": SEED,
-                "rows": n, "nnz": nnz_total, "offset_bits": local.Ap.element_size() * 8,
+                "rows": n, "nnz": nnz_total, "offset_bits": offset_bits,
                 "algorithmic_bytes_per_spmv": alg_bytes_total,
                 "step": "one power-iteration SpMV (x <- A x / ||A x||) over the whole matrix, "
                         "incl. x exchange and norm",
                 "kind": args.kind, "selected_kernel": kind_names.get(stats["chosen_kind"]),
-                "exchange": it.exchange, "exchange_note": getattr(it, "exchange_note", ""), "parallelism": f"row-sharded x{world} (merge-path nnz split, row weight {args.row_weight}"
+                "exchange": exchange_used, "exchange_note": exchange_note, "parallelism": f"row-sharded x{world} (merge-path nnz split, row weight {args.row_weight}"
                                 + (f", re-split {args.rebalance}x from measured per-rank local step times)" if world > 1 and args.rebalance else ")"),
                 "rebalance": rebalance_log,
                 "l2": "inputs larger than L2 (no flush needed)" if alg_bytes_total > 4 * 126e6
                       else "inputs smaller than L2: steps run back to back, L2-warm",
                 "generation_s": t_gen, "eigen_estimate": eig,
                 "row_stats": {k: stats[k] for k in ("max_row_len", "mean_row_len", "std_row_len", "empty_rows")},
+                "hot_x": dict(hot, note="merge-path kernel gathers the most frequent columns from a dense "
+                              "copy refilled from x every step (csrc/hotx.cu); plan built once, outside the timed region"),
                 "per_rank": {"kernel_ms": [round(r[0], 4) for r in per_rank],
                              "rows": [int(r[1]) for r in per_rank], "nnz": [int(r[2]) for r in per_rank]},
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                         "traffic_note": traffic_note,
                          "peak_source": peak_src, "kernel_ms": kern_ms,
-                         "kernel": f"{kind_names.get(stats['chosen_kind'])} main kernel, rank 0 shard",
+                         "kernel": f"{main_kernel} ({kind_names.get(stats['chosen_kind'])} main kernel), rank 0 shard",
                          "algorithmic_bytes_per_launch": alg_bytes_local,
                          "kernel_share_of_step": kern_ms / (elapsed_ms / args.steps),
+                         "non_kernel_ms": elapsed_ms / args.steps - kern_ms,
                          "frac_of_datasheet_8000": (achieved / 8000.0) if achieved else None},
             "cpu_baseline": cpu_info,
+            "parity": parity,
+            "configs": configs,
             "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clocks,

@@ -40,12 +40,5 @@ inline void CheckSpmvStatus(int status, char const *const func, const char *cons
 }
 #define checkSpmvStatus(val) CheckSpmvStatus((val), #val, __FILE__, __LINE__)
 
-// The stream every kind enqueues on (the reference uses the legacy default stream
-// everywhere; so does this, unless the caller sets another one).
-struct SpmvStream {
-    static cudaStream_t &get() {
-        static cudaStream_t s = nullptr;
-        return s;
-    }
-    static void set(cudaStream_t s) { get() = s; }
-};
+// SpmvStream (the stream every kind enqueues on) lives in timer.hpp, beside the Timer that
+// records its events on it.

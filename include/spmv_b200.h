@@ -239,6 +239,12 @@ SPMVB200_API int64_t spmvb200_launch_count(void);
 /* drop cached scratch / statistics (all devices) */
 SPMVB200_API void spmvb200_release_cache(void);
 
+/* Measurement aid (csrc/diag.cu): `gathers` uniformly random 4-byte gathers of an x of
+ * `x_elements` floats, the index stream read as the kernels read Aj -- the gather rate every CSR
+ * kernel that gathers x through L1 is bounded by.  Best of `reps` launches, in milliseconds. */
+SPMVB200_API int spmvb200_gather_yardstick(int64_t x_elements, int64_t gathers, int reps,
+                                           spmvb200_stream_t stream, double *best_ms);
+
 /* The hot-x plan of the merge-path kernel (csrc/hotx.cu): for an x far longer than the TLB and L2
  * reach (option "hot_x_min_bytes", 256 MB) and a caller that passes SPMVB200_FLAG_STATIC_PATTERN,
  * the library keeps a copy of Aj in which the most frequent columns are renumbered into one dense

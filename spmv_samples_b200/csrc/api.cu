@@ -308,6 +308,11 @@ void spmvb200_release_cache(void) {
     scratch_release_all();
 }
 
+int spmvb200_gather_yardstick(int64_t x_elements, int64_t gathers, int reps, spmvb200_stream_t stream,
+                              double *best_ms) {
+    return gather_yardstick(x_elements, gathers, reps, static_cast<cudaStream_t>(stream), best_ms);
+}
+
 int spmvb200_hot_x_info(const int32_t *Aj, int64_t *hot_columns, double *hot_share, double *build_ms) {
     // never builds: nnz / n_cols are not needed to look a plan up, so find it by address alone
     if (hot_columns) *hot_columns = 0;

@@ -155,6 +155,8 @@ void hot_plan_clear();
 void hot_plan_drop(const int32_t *Aj);
 const HotPlan *hot_plan_peek(const int32_t *Aj);  // the plan built for this Aj on the current device, or nullptr
 
+int gather_yardstick(int64_t n_x, int64_t count, int reps, cudaStream_t stream, double *best_ms);
+
 // Launch attribute helper: optional L2 access-policy window over x (option "l2_window").
 struct LaunchCfg {
     cudaLaunchConfig_t cfg;

@@ -57,7 +57,7 @@ std::map<std::string, int64_t> &options() {
                                  // "hot_x_min_bytes"; 0 = never; 1 = always (plan keyed on the Aj pointer)
         {"hot_x_min_bytes", 256ll << 20},
         {"hot_x_max_bytes", 32ll << 20},   // size of the dense copy of the hot columns' x
-        {"stream_ctas_per_sm", 2},  // persistent CTAs per SM of the CSR-stream kernel
+        {"stream_ctas_per_sm", 3},  // persistent CTAs per SM of the CSR-stream kernel
         {"cusparse_alg", 0},     // 0: CUSPARSE_SPMV_ALG_DEFAULT (the reference's call), 1: CSR_ALG1, 2: CSR_ALG2
     };
     return o;

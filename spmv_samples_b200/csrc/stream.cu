@@ -27,14 +27,35 @@ namespace spmvb200 {
 
 namespace {
 
-constexpr int kRows = 256;                   // rows per tile = consumer threads
+#ifndef SPMV_STREAM_ROWS
+#define SPMV_STREAM_ROWS 256
+#endif
+#ifndef SPMV_STREAM_CAP
+#define SPMV_STREAM_CAP 2048
+#endif
+#ifndef SPMV_STREAM_STAGES
+#define SPMV_STREAM_STAGES 3
+#endif
+// ablation builds only (tools/build_variants.sh): 1 = no x gathers, 2 = consumers only take and
+// release stages (the TMA stream alone), 3 = as 2 and no row offsets staged
+#ifndef SPMV_STREAM_ABLATE
+#define SPMV_STREAM_ABLATE 0
+#endif
+constexpr int kRows = SPMV_STREAM_ROWS;      // rows per tile = consumer threads
 constexpr int kConsumerWarps = kRows / 32;
 constexpr int kStreamBlock = kRows + 32;     // + one producer warp
-constexpr int kCap = 2048;                   // nonzeros per stage
-constexpr int kStages = 3;
+constexpr int kCap = SPMV_STREAM_CAP;        // nonzeros per stage
+constexpr int kStages = SPMV_STREAM_STAGES;
+#ifndef SPMV_STREAM_ALIGN
+#define SPMV_STREAM_ALIGN 32
+#endif
+constexpr int kAlign = SPMV_STREAM_ALIGN;    // a stage's Aj / Ax copies start at a multiple of this many
+                                             // nonzeros: 32 = 128 bytes of Aj (16-byte starts ran the
+                                             // TMA stream at 2.5 TB/s on the Laplacian)
+static_assert(kAlign % 4 == 0 && kCap % kAlign == 0, "stage geometry");
 
 struct alignas(16) StageMeta {
-    long long abase;      // nonzero index held by slot 0 of the stage's Aj / Ax buffers (4-aligned)
+    long long abase;      // nonzero index held by slot 0 of the stage's Aj / Ax buffers (kAlign-aligned)
     long long lo, hi;     // the stage holds the tile's nonzeros [lo, hi)
     int row0;             // first row of the tile
     int rows;             // rows in the tile (0 = end of this CTA's work)
@@ -43,12 +64,14 @@ struct alignas(16) StageMeta {
 
 template <typename OffT, typename ValT>
 struct StreamSmem {
-    static constexpr int kOffPad = 16 / sizeof(OffT);
-    static constexpr size_t off_bytes = (size_t)(kRows + kOffPad) * sizeof(OffT);
+    // every staged array starts on a 128-byte boundary of shared memory (and of global memory,
+    // see kAlign): the bulk-copy engine moves whole 128-byte lines that way
+    static constexpr size_t off_bytes = ((size_t)(kRows + 1) * sizeof(OffT) + 127) / 128 * 128;
     static constexpr size_t col_bytes = (size_t)kCap * sizeof(int32_t);
     static constexpr size_t val_bytes = (size_t)kCap * sizeof(ValT);
     static constexpr size_t stage_bytes = off_bytes + col_bytes + val_bytes;
-    static constexpr size_t total = 128 + sizeof(StageMeta) * kStages + stage_bytes * kStages;
+    static constexpr size_t header = (128 + sizeof(StageMeta) * kStages + 127) / 128 * 128;
+    static constexpr size_t total = header + stage_bytes * kStages;
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
@@ -66,7 +89,7 @@ stream_kernel(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap, const int32
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);  // [kStages]
     uint64_t *empty = full + kStages;                         // [kStages]
     StageMeta *meta = reinterpret_cast<StageMeta *>(smem_raw + 128);
-    unsigned char *stages = smem_raw + 128 + sizeof(StageMeta) * kStages;
+    unsigned char *stages = smem_raw + L::header;
     auto s_off = [&](int s) { return reinterpret_cast<OffT *>(stages + (size_t)s * L::stage_bytes); };
     auto s_col = [&](int s) { return reinterpret_cast<int32_t *>(stages + (size_t)s * L::stage_bytes + L::off_bytes); };
     auto s_val = [&](int s) {
@@ -111,7 +134,7 @@ stream_kernel(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap, const int32
                 const long long E = __shfl_sync(0xffffffffu, bounds, j + 1);
                 const int64_t row0 = tile * kRows;
                 const int rows = (int)(((int64_t)n_rows - row0) < kRows ? ((int64_t)n_rows - row0) : kRows);
-                const long long abase0 = B & ~3ll;
+                const long long abase0 = B & ~(long long)(kAlign - 1);
                 const long long span = E - abase0;
                 const int chunks = span > 0 ? (int)((span + kCap - 1) / kCap) : 1;
                 for (int ch = 0; ch < chunks; ++ch, ++it) {
@@ -198,16 +221,23 @@ stream_kernel(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap, const int32
         const ValT *vs = s_val(s);
         // four nonzeros per trip: their gathers are in flight together, the additions stay in
         // the order of the row
+#if SPMV_STREAM_ABLATE >= 2
+        if (lo < 0)
+#endif
         for (int i = lo; i < hi; i += 4) {
             const int n = hi - i;
             const int c0 = cs[i];
             const int c1 = n > 1 ? cs[i + 1] : c0;
             const int c2 = n > 2 ? cs[i + 2] : c0;
             const int c3 = n > 3 ? cs[i + 3] : c0;
+#if SPMV_STREAM_ABLATE == 1
+            const ValT x0 = (ValT)c0, x1 = (ValT)c1, x2 = (ValT)c2, x3 = (ValT)c3;
+#else
             const ValT x0 = ldg_hint(x + c0, pol_x);
             const ValT x1 = ldg_hint(x + c1, pol_x);
             const ValT x2 = ldg_hint(x + c2, pol_x);
             const ValT x3 = ldg_hint(x + c3, pol_x);
+#endif
             sum += vs[i] * x0;
             if (n > 1) sum += vs[i + 1] * x1;
             if (n > 2) sum += vs[i + 2] * x2;
@@ -239,12 +269,17 @@ int launch_stream(const SpmvProblem<OffT, ValT> &p) {
         SPMV_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
         configured[has_peers] = true;
     }
-    // persistent grid: "stream_ctas_per_sm" CTAs per SM (default 2: two rings of stages per SM keep
-    // one streaming while the other's consumers wait on x), never more CTAs than tiles
-    int64_t per_sm = option_get("stream_ctas_per_sm", 2);
+    // persistent grid: "stream_ctas_per_sm" CTAs per SM, never more CTAs than tiles.  Measured on
+    // the 1024^2 Laplacian (L2 flushed): 1 -> 30.7 us, 2 -> 21.5, 3 -> 20.5, 4 -> 24.6 (shared memory
+    // squeezes the L1 the gathers need); the stage geometry (256/512-row tiles, 3-6 stages) moves
+    // nothing, and with the consumers switched off the TMA stream alone takes 18.4 us: what is left
+    // is launch + two dependent DRAM round trips before the first tile arrives.
+    int64_t per_sm = option_get("stream_ctas_per_sm", 3);
     if (per_sm < 1) per_sm = 1;
-    const int64_t max_fit = (int64_t)(di->smem_optin / L::total) > 0 ? (int64_t)(di->smem_optin / L::total) : 1;
-    if (per_sm > max_fit) per_sm = max_fit;
+    int occ = 1;
+    SPMV_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kStreamBlock, L::total));
+    if (occ < 1) occ = 1;
+    if (per_sm > occ) per_sm = occ;
     int64_t grid = (int64_t)di->sm_count * per_sm;
     if (grid > num_tiles) grid = num_tiles;
     LaunchCfg lc;

@@ -308,3 +308,13 @@ def hot_x_info(Aj) -> dict:
 
 def release_cache() -> None:
     _lib.lib().spmvb200_release_cache()
+
+
+def gather_yardstick(x_elements: int, gathers: int = 1 << 27, reps: int = 3, stream=None) -> float:
+    """G gathers/s of nothing but uniformly random 4-byte gathers over x_elements floats
+    (csrc/diag.cu): the yardstick beside the gather-bound configurations."""
+    ms = C.c_double(0.0)
+    st = _lib.lib().spmvb200_gather_yardstick(int(x_elements), int(gathers), int(reps),
+                                              _stream_ptr(stream), C.byref(ms))
+    _lib.check(st, "spmvb200_gather_yardstick")
+    return gathers / (ms.value * 1e-3) / 1e9

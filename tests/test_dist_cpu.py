@@ -156,3 +156,45 @@ def test_host_buffer_front_ends_refuse_to_run_without_cuda():
         ShardedHostSpMV(shard, 2)
     with pytest.raises(RuntimeError, match="CUDA"):
         PowerIteration(shard, 2)
+
+
+# ------------------------------------------------------------------ host-I/O redistribution
+def test_overlap_sizes_partition_both_ways():
+    """ShardedHostSpMV moves y from the compute partition (uneven, nnz-balanced) to the even
+    host-I/O partition with one all-to-all: the send splits of all ranks must tile every
+    destination slice exactly, in row order."""
+    from spmv_samples_b200.dist import even_bounds, overlap_sizes
+    for n, rb in ((100, [0, 3, 50, 51, 100]), (17, [0, 0, 17, 17, 17]), (8, [0, 2, 4, 6, 8]), (5, [0, 5, 5, 5, 5])):
+        w = len(rb) - 1
+        io = even_bounds(n, w)
+        assert io[0] == 0 and io[-1] == n and all(b - a in (n // w, n // w + 1) for a, b in zip(io, io[1:]))
+        send = [overlap_sizes(rb, p, io) for p in range(w)]
+        recv = [overlap_sizes(io, q, rb) for q in range(w)]
+        for p in range(w):
+            assert sum(send[p]) == rb[p + 1] - rb[p]
+            for q in range(w):
+                assert send[p][q] == recv[q][p]
+        for q in range(w):
+            assert sum(recv[q]) == io[q + 1] - io[q]
+
+
+def _a2a_worker(rank, world, port, out_dir):
+    from spmv_samples_b200.dist import even_bounds, overlap_sizes
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, rb = 1001, [0, 13, 700, 1001][:world] + [1001]
+    rb = [0, 13, 1001] if world == 2 else [0, 13, 700, 1001]
+    io = even_bounds(n, world)
+    y_full = torch.arange(n, dtype=torch.float32) * 0.5
+    mine = y_full[rb[rank]:rb[rank + 1]].clone()                 # the rows this rank "computed"
+    out = torch.full((io[rank + 1] - io[rank],), float("nan"))
+    dist.all_to_all_single(out, mine, output_split_sizes=overlap_sizes(io, rank, rb),
+                           input_split_sizes=overlap_sizes(rb, rank, io))
+    assert torch.equal(out, y_full[io[rank]:io[rank + 1]])
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_all_to_all_moves_rows_between_partitions(world, tmp_path):
+    mp.spawn(_a2a_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)

@@ -199,7 +199,8 @@ def _host_rank_main(rank, world, port, out_dir):
     m = gen.rmat(14, 16, 7, offset=torch.int64)
     shard = shard_rows(m, rank, world)
     hs = ShardedHostSpMV(shard, m.n_rows, kind="auto", slots=3)
-    r0, r1 = shard.row_begin, shard.row_end
+    r0, r1 = hs.io_begin, hs.io_end        # even host slices, whatever rows the rank computes
+    assert (r0, r1) == (rank * m.n_rows // world, (rank + 1) * m.n_rows // world)
     xs = [torch.from_numpy(g.gen_x(200 + i, m.n_cols)[r0:r1].copy()).pin_memory() for i in range(7)]
     ys = [torch.full((r1 - r0,), float("nan")).pin_memory() for _ in range(7)]
     hs.spmv_many(xs, ys)

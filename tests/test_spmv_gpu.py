@@ -633,7 +633,7 @@ def test_stream_sums_in_row_order():
     try:
         y1 = run_kind("stream", Ap, Aj, Ax, x)
     finally:
-        spmv.set_option("stream_ctas_per_sm", 2)
+        spmv.set_option("stream_ctas_per_sm", 3)
     assert np.array_equal(y1, y2)
 
 
