@@ -210,32 +210,39 @@ def build_row_sample(m, sample_nnz_target, n_blocks=16):
     return Ap, Aj, Ax, rows_total
 
 
-def cpu_reference_leg(global_csr, x_dev, steps, warmup, seconds_budget, sample_nnz_target=1 << 26):
-    """Time the reference's CPU CSR loop on a bounded sample of the matrix, all host threads,
-    for exactly `steps` timed calls after `warmup`.  The sample (see build_row_sample) is shrunk
-    until warmup + steps calls fit the time budget; x is the full vector, so the gathers miss
-    the CPU caches the way the full problem's do.  Returns (gflops, info dict)."""
+def time_cpu_reference(Ap, Aj, Ax, x, rows_total, steps, warmup, seconds_budget):
+    """Time the reference's CPU CSR loop on a host CSR sample, all host threads, for exactly
+    `steps` timed calls after `warmup`.  If warmup + steps calls would not fit the time budget the
+    sample is cut to a prefix of its rows (x stays full length, so the gathers miss the CPU caches
+    the way the full problem's do).  Returns (gflops, info dict)."""
     import numpy as np
 
     from oracle import cpu
 
-    x = x_dev.cpu().numpy()
     threads = os.cpu_count() or 1
     total = warmup + steps
-    target = sample_nnz_target
+    use_ref = cpu.have_ref() and not (Ap.dtype == np.int64 and Ax.dtype == np.float64)
+    rows_all, nnz_all = rows_total, int(Ap[-1])
+
+    def runner(Ap_, Aj_, Ax_):
+        return (lambda: cpu.ref_spmv_mt(Ap_, Aj_, Ax_, x, threads)) if use_ref else \
+               (lambda: cpu.spmv_mt(Ap_, Aj_, Ax_, x, threads))
+
+    run = runner(Ap, Aj, Ax)
     while True:
-        Ap, Aj, Ax, rows_total = build_row_sample(global_csr, target)
-        nnz_s = int(Ap[-1])
-        use_ref = cpu.have_ref() and not (Ap.dtype == np.int64 and Ax.dtype == np.float64)
-        run = (lambda: cpu.ref_spmv_mt(Ap, Aj, Ax, x, threads)) if use_ref else \
-              (lambda: cpu.spmv_mt(Ap, Aj, Ax, x, threads))
         run()                                 # first touch
         t0 = time.perf_counter()
         _, used = run()                       # calibration
         t_one = time.perf_counter() - t0
-        if t_one * total <= seconds_budget or target <= (1 << 20):
+        nnz_s = int(Ap[-1])
+        if t_one * total <= seconds_budget or nnz_s <= (1 << 20):
             break
-        target = max(1 << 20, int(target * seconds_budget / (t_one * total) * 0.8))
+        keep = max(1 << 20, int(nnz_s * seconds_budget / (t_one * total) * 0.8))
+        r = max(1, int(np.searchsorted(Ap, keep, side="right")) - 1)
+        Ap = np.ascontiguousarray(Ap[:r + 1])
+        Aj, Ax = Aj[:int(Ap[-1])], Ax[:int(Ap[-1])]
+        rows_total = r
+        run = runner(Ap, Aj, Ax)
     for _ in range(max(0, warmup - 2)):
         run()
     t0 = time.perf_counter()
@@ -253,15 +260,118 @@ def cpu_reference_leg(global_csr, x_dev, steps, warmup, seconds_budget, sample_n
         "kind": "reference" if use_ref else "port",
         "cores": int(used),
         "host_cores": int(threads),
-        "sample": f"{rows_total} rows / {nnz_s} nonzeros in 16 equally spaced row blocks of the "
-                  f"workload matrix, full-length x, {steps} timed calls of "
+        "sample": f"{rows_total} rows / {nnz_s} nonzeros"
+                  + (f" (cut from {rows_all} / {nnz_all} to fit the time budget)" if nnz_s != nnz_all else "")
+                  + " in equally spaced row blocks of the workload matrix, full-length x, "
+                  f"{steps} timed calls of "
                   + ("reference SpMV_cpu_navie (oracle/_ref) on row blocks from all host threads"
                      if use_ref else "the oracle port of SpMV_cpu_navie, row blocks on all host threads"),
+        "sample_rows": int(rows_total), "sample_nnz": int(nnz_s),
         "single_thread_value": 2.0 * nnz_s / dt1 / 1e9,
         "steps": steps,
         "ms_per_step": dt * 1e3,
     }
     return 2.0 * nnz_s / dt / 1e9, info
+
+
+def cpu_reference_leg(global_csr, x_dev, steps, warmup, seconds_budget, sample_nnz_target=1 << 26):
+    """cpu_baseline leg of the own arm: sample the resident matrix, time the reference on it."""
+    Ap, Aj, Ax, rows_total = build_row_sample(global_csr, sample_nnz_target)
+    return time_cpu_reference(Ap, Aj, Ax, x_dev.cpu().numpy(), rows_total, steps, warmup, seconds_budget)
+
+
+# --------------------------------------------------------------------------- reference arm
+SAMPLER_SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, {root!r})
+import bench
+from spmv_samples_b200 import generate
+torch.cuda.set_device(0)
+m = generate.make_config({workload!r}, bench.SEED, scale_override={override!r})
+x = generate.gen_x(m.n_cols, bench.SEED, m.Ax.dtype)
+Ap, Aj, Ax, rows = bench.build_row_sample(m, {target}, n_blocks=64)
+np.save({out!r} + "/Ap.npy", Ap); np.save({out!r} + "/Aj.npy", Aj); np.save({out!r} + "/Ax.npy", Ax)
+np.save({out!r} + "/x.npy", x.cpu().numpy())
+np.save({out!r} + "/meta.npy", np.array([rows, m.n_rows, m.nnz, m.Ap.element_size() * 8, m.algorithmic_bytes()], dtype=np.int64))
+"""
+
+
+def sample_in_subprocess(args, target_nnz):
+    """The workload's matrix only exists as a device generator (csrc/gen.cu); the reference arm must
+    not have this repository's library in the process it times.  So a child process generates the
+    matrix on the GPU, cuts the row sample and leaves it on disk; the timed process only ever loads
+    numpy arrays and oracle/_ref."""
+    import subprocess
+    import tempfile
+
+    import numpy as np
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    out = tempfile.mkdtemp(prefix="spmv_ref_sample_", dir=base)
+    code = SAMPLER_SCRIPT.format(root=ROOT, workload=args.workload, override=(args.override or None),
+                                 target=int(target_nnz), out=out)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
+    if r.returncode != 0:
+        raise RuntimeError("sampler subprocess failed: " + (r.stderr or "")[-400:])
+    arrs = {k: np.load(os.path.join(out, k + ".npy")) for k in ("Ap", "Aj", "Ax", "x", "meta")}
+    import shutil
+    shutil.rmtree(out, ignore_errors=True)
+    return arrs
+
+
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return 0
+    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+    have_gpu = False
+    try:
+        import subprocess
+        have_gpu = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=30).returncode == 0
+    except Exception:
+        have_gpu = False
+    note = None
+    if have_gpu:
+        # 2^28 nonzeros = 12.5 % of the workload's 2^31, in 64 equally spaced row blocks
+        a = sample_in_subprocess(args, 1 << 28)
+        Ap, Aj, Ax, x = a["Ap"], a["Aj"], a["Ax"], a["x"]
+        rows_s, n_rows, nnz, off_bits, alg_bytes = (int(v) for v in a["meta"])
+    else:
+        # no GPU, no device generator: the host restatement at a scale the host can build
+        import numpy as np
+
+        from oracle import generators as g
+        scale = 20
+        Ap, Aj, Ax = g.rmat(scale, 16, SEED, offset_dtype=np.int64)
+        x = g.gen_x(SEED, 1 << scale)
+        rows_s, n_rows, nnz, off_bits = 1 << scale, 1 << scale, int(Ap[-1]), 64
+        alg_bytes = nnz * 8 + (n_rows + 1) * 8 + n_rows * 8
+        note = f"no GPU: R-MAT scale {scale} generated on the host instead of the workload"
+    value, info = time_cpu_reference(Ap, Aj, Ax, x, rows_s, args.steps, args.warmup, seconds_budget=150.0)
+    info["value"] = value
+    info["unit"] = UNIT
+    info["sample_fraction_of_nnz"] = info["sample_nnz"] / max(nnz, 1)
+    line.update({
+        "value": value,
+        "ms_per_step": info["ms_per_step"],
+        "steps": info["steps"],
+        "config": {"workload": workload_desc(args.workload, args.override), "seed": SEED,
+                   "rows": n_rows, "nnz": nnz, "offset_bits": off_bits,
+                   "algorithmic_bytes_per_spmv": alg_bytes,
+                   "step": "one CPU CSR SpMV (reference SpMV_cpu_navie) over a bounded row sample of the "
+                           "workload matrix; GFLOP/s = 2 * sample nnz / time, a rate comparable with the "
+                           "own arm's 2 * nnz / time",
+                   "kind": "reference/include/spmv/cpu_navie.hpp:3-17 compiled by oracle/Makefile",
+                   "sample_fraction_of_nnz": info["sample_fraction_of_nnz"],
+                   "process": "this process never loads libspmvb200.so: a child process generated the "
+                              "matrix and cut the sample" if have_gpu else "host-generated sample",
+                   "note": note},
+        "cpu_baseline": info,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    })
+    print(json.dumps(line), flush=True)
+    return 0
 
 
 # --------------------------------------------------------------------------- parity leg
@@ -406,49 +516,6 @@ def configs_leg(peak, iters=15):
     del flush
     torch.cuda.empty_cache()
     return out
-
-
-# --------------------------------------------------------------------------- reference arm
-def reference_arm(args, rank, world):
-    if rank != 0:
-        return 0
-    import torch
-
-    from spmv_samples_b200 import generate
-    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
-    if not torch.cuda.is_available():
-        # the matrix generator is a device kernel; without a GPU fall back to the host
-        # restatement at a scale the host can build
-        from oracle import generators as g
-        import numpy as np
-        scale = 20
-        Ap, Aj, Ax = g.rmat(scale, 16, SEED, offset_dtype=np.int64)
-        m = generate.Csr(1 << scale, 1 << scale, int(Ap[-1]), torch.from_numpy(Ap), torch.from_numpy(Aj),
-                         torch.from_numpy(Ax), f"rmat_s{scale} (host generated: no GPU)")
-        x = torch.from_numpy(g.gen_x(SEED, 1 << scale))
-        note = f"no GPU: R-MAT scale {scale} generated on the host instead of the workload"
-    else:
-        torch.cuda.set_device(0)
-        m = generate.make_config(args.workload, SEED, scale_override=args.override or None)
-        x = generate.gen_x(m.n_cols, SEED, m.Ax.dtype)
-        note = None
-    value, info = cpu_reference_leg(m, x, args.steps, args.warmup, seconds_budget=150.0)
-    info["value"] = value
-    info["unit"] = UNIT
-    line.update({
-        "value": value,
-        "ms_per_step": info["ms_per_step"],
-        "steps": info["steps"],
-        "config": {"workload": workload_desc(args.workload, args.override), "seed": SEED,
-                   "step": "one CPU CSR SpMV over the bounded sample", "note": note},
-        "cpu_baseline": info,
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    })
-    print(json.dumps(line), flush=True)
-    return 0
 
 
 # --------------------------------------------------------------------------- own arm

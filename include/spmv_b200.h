@@ -316,6 +316,55 @@ SPMVB200_API int spmvb200_sum_squares(int value_bits, int64_t n, const void *v, 
 SPMVB200_API int spmvb200_inv_sqrt(int value_bits, const double *sumsq_dev, void *alpha_dev,
                                    spmvb200_stream_t stream);
 
+/* Everything between two SpMVs of the row-sharded power iteration in ONE kernel: sum of squares
+ * of this rank's `n` values of y, exchange of the per-rank sums, *sumsq_dev = their total (added
+ * in rank order: the same bits on every rank), *alpha_dev = 1 / sqrt(total).  Mailboxes:
+ * SPMVB200_MAILBOX_BYTES of device memory per rank, filled with the double -1.0 once before the
+ * first step, each mapped into every other rank (cudaIpc / peer access / symmetric memory).
+ * mailbox_of_rank[q] (HOST array of `world` DEVICE pointers) is rank q's mailbox as addressed
+ * from this rank, [rank] being mailbox_local itself; or mailbox_multicast is one NVLink multicast
+ * address that reaches all of them (then mailbox_of_rank may be NULL).  `step` counts up from 0
+ * by one per call, in step on all ranks.  Leaving the kernel means every rank has finished the
+ * kernels it enqueued before its own call for this step -- the step barrier of the fused
+ * exchange.  A rank that does not arrive within ~4 s sets *error_dev (DEVICE int, zero it once)
+ * to 1 + its number on the ranks that waited for it, instead of hanging them.
+ * The reference has no iteration and no exchange (main.cu:102-113 repeats one call). */
+#define SPMVB200_MAILBOX_BYTES 256
+SPMVB200_API int spmvb200_norm_exchange(int value_bits, int64_t n, const void *y_local, int rank,
+                                        int world, uint64_t step, void *mailbox_local,
+                                        void *const *mailbox_of_rank, void *mailbox_multicast,
+                                        double *sumsq_dev, void *alpha_dev, int *error_dev,
+                                        spmvb200_stream_t stream);
+
+/* ---- the row-sharded power iteration from ONE process (csrc/multi.cu) ----------------------
+ * BASELINE.json's multi-GPU configuration for a C / C++ host (main.cu --gpus N): no Python, no
+ * torch.distributed, no NCCL.  The matrix (square) is cut into `n_gpus` row blocks at the merge
+ * path's nnz-balanced boundaries; GPU g keeps its block and two full-length replicas of x; a step
+ * is the SpMV of the local rows, whose row stores also go into every other GPU's replica of the
+ * next x through peer access over NVLink (the all-gather is the kernel's epilogue), followed by
+ * spmvb200_norm_exchange (norm, alpha and step barrier in one kernel).  devices = NULL means
+ * 0 .. n_gpus-1; every pair must be peer-accessible (SPMVB200_ERR_UNSUPPORTED otherwise).
+ * create_from_device takes CSR arrays resident on devices[0] (not kept: each GPU gets its own
+ * copy of its rows); create takes HOST arrays.  steps enqueues and returns; run times `steps`
+ * steps on the devices (the slowest GPU counts) and synchronises; get returns the current
+ * iterate (n values, HOST, may be NULL), ||A x_k|| of the last step and the n_gpus + 1 row
+ * boundaries (HOST int64, may be NULL). */
+typedef struct spmvb200_power spmvb200_power_t;
+SPMVB200_API int spmvb200_power_create(int n_gpus, const int *devices, int offset_bits, int value_bits,
+                                       int64_t n_rows, int64_t nnz, const void *Ap_host,
+                                       const int32_t *Aj_host, const void *Ax_host, int kind,
+                                       spmvb200_power_t **out);
+SPMVB200_API int spmvb200_power_create_from_device(int n_gpus, const int *devices, int offset_bits,
+                                                   int value_bits, int64_t n_rows, int64_t nnz,
+                                                   const void *Ap_dev, const int32_t *Aj_dev,
+                                                   const void *Ax_dev, int kind, spmvb200_power_t **out);
+SPMVB200_API int spmvb200_power_reset(spmvb200_power_t *p);
+SPMVB200_API int spmvb200_power_steps(spmvb200_power_t *p, int steps);
+SPMVB200_API int spmvb200_power_run(spmvb200_power_t *p, int steps, double *ms_per_step);
+SPMVB200_API int spmvb200_power_sync(spmvb200_power_t *p);
+SPMVB200_API int spmvb200_power_get(spmvb200_power_t *p, void *x_host, double *norm, int64_t *row_bounds);
+SPMVB200_API void spmvb200_power_destroy(spmvb200_power_t *p);
+
 /* ---- device timing of the dominant kernel (bench.py's roofline.achieved) ------------------
  * With option "time_main_kernel" = 1 every merge / vector / light call brackets its main
  * kernel with cudaEvents on the caller's stream.  This call synchronises on them, returns the

@@ -16,6 +16,8 @@
 //   * the host CSR loop is timed too (one thread, like the reference's), as a reported baseline.
 // Options: --iters N (default 2000, reference/main.cu:19)   --x ones|random (default ones,
 //   reference/main.cu:41)   --flush (evict L2 between timed calls)   --peak GBps
+//   --power K [--gpus N]: K power-iteration steps, the matrix row-sharded over N GPUs of the box
+//   (one process, peer access; csrc/multi.cu) -- the multi-GPU configuration without Python
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -48,6 +50,8 @@ struct Options {
                                // the working directory, or --peak, overrides it
     double datasheet_gbs = 8000.0;
     uint64_t seed = 0x5EEDB200ull;
+    int gpus = 1;    // --gpus N: the row-sharded power iteration over N GPUs of this box
+    int power = 0;   // --power K: K power-iteration steps x <- A x / ||A x|| (BASELINE.json configs[4])
 };
 
 template <typename T>
@@ -161,6 +165,31 @@ static int run(const Options &opt, const string &name, index_t n_rows, index_t n
 
     checkCudaErr(cudaEventDestroy(loop_begin));
     checkCudaErr(cudaEventDestroy(loop_end));
+    //--------------------------------------------------------------------------
+    // power iteration, row-sharded over --gpus GPUs from this one process (csrc/multi.cu): the
+    // matrix goes from this device to the others by peer copies; the iteration itself never
+    // returns to the host
+    if (opt.power > 0 && n_rows == n_cols) {
+        spmvb200_power_t *pw = nullptr;
+        checkSpmvStatus(spmvb200_power_create_from_device(opt.gpus, nullptr, sizeof(offset_t) * 8, sizeof(value_t) * 8,
+                                                          n_rows, (int64_t)nnz, dA_csrOffsets, dA_columns, dA_values,
+                                                          SPMVB200_KIND_AUTO, &pw));
+        double ms = 0, norm = 0;
+        checkSpmvStatus(spmvb200_power_run(pw, 5, &ms));   // warm-up: scratch, statistics, hot-x plan
+        checkSpmvStatus(spmvb200_power_reset(pw));
+        checkSpmvStatus(spmvb200_power_run(pw, opt.power, &ms));
+        vector<int64_t> rb((size_t)opt.gpus + 1);
+        checkSpmvStatus(spmvb200_power_get(pw, nullptr, &norm, rb.data()));
+        printf("Power iteration (%d steps, %d GPU%s, kind auto):\n", opt.power, opt.gpus, opt.gpus > 1 ? "s" : "");
+        printf("[%-12s] %12lf ms/step  %9.1f GFLOP/s  %8.1f GB/s  %5.1f%% of measured %.0f GB/s x %d  ||A x|| = %.9g\n",
+               "power", ms, flops / (ms * 1e-3) / 1e9, bytes / (ms * 1e-3) / 1e9,
+               100.0 * bytes / (ms * 1e-3) / 1e9 / (opt.peak_gbs * opt.gpus), opt.peak_gbs, opt.gpus, norm);
+        printf("[%-12s] rows per GPU:", "split");
+        for (int g = 0; g < opt.gpus; ++g) printf(" %lld", (long long)(rb[(size_t)g + 1] - rb[(size_t)g]));
+        printf("\n");
+        spmvb200_power_destroy(pw);
+    }
+
     if (flush_buf) checkCudaErr(cudaFree(flush_buf));
     checkCudaErr(cudaFree(dX));
     checkCudaErr(cudaFree(dY));
@@ -251,7 +280,7 @@ static int run_synthetic(const Options &opt, const string &cfg, long size) {
 int main(int argc, char **argv) {
     if (argc < 3) {
         cerr << "usage: ./bin/<program-name>  <filename.mtx | synthetic:c1..c5[:size]>  <SpMV_kind_string>..."
-                "  [--iters N] [--x ones|random] [--flush] [--peak GB/s]"
+                "  [--iters N] [--x ones|random] [--flush] [--peak GB/s] [--power K [--gpus N]]"
              << endl;
         exit(1);
     }
@@ -263,6 +292,8 @@ int main(int argc, char **argv) {
         else if (a == "--x" && i + 1 < argc) opt.random_x = string(argv[++i]) == "random";
         else if (a == "--flush") opt.flush = true;
         else if (a == "--peak" && i + 1 < argc) opt.peak_gbs = atof(argv[++i]);
+        else if (a == "--gpus" && i + 1 < argc) opt.gpus = atoi(argv[++i]);
+        else if (a == "--power" && i + 1 < argc) opt.power = atoi(argv[++i]);
         else opt.kinds.push_back(a);
     }
     if (opt.kinds.empty() || opt.iters < 1) {

@@ -124,6 +124,19 @@ def lib() -> C.CDLL:
     L.spmvb200_matrix_create_from_device.argtypes = L.spmvb200_matrix_create.argtypes
     L.spmvb200_sum_squares.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.spmvb200_inv_sqrt.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.spmvb200_power_create.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int64, C.c_int64,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.spmvb200_power_create_from_device.argtypes = L.spmvb200_power_create.argtypes
+    L.spmvb200_power_reset.argtypes = [C.c_void_p]
+    L.spmvb200_power_steps.argtypes = [C.c_void_p, C.c_int]
+    L.spmvb200_power_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+    L.spmvb200_power_sync.argtypes = [C.c_void_p]
+    L.spmvb200_power_get.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    L.spmvb200_power_destroy.argtypes = [C.c_void_p]
+    L.spmvb200_power_destroy.restype = None
+    L.spmvb200_norm_exchange.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_uint64,
+                                         C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]
     L.spmvb200_main_kernel_time.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.spmvb200_device_malloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
     L.spmvb200_device_free.argtypes = [C.c_void_p]

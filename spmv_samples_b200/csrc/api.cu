@@ -346,6 +346,9 @@ struct spmvb200_matrix {
 namespace spmvb200 {
 template <typename ValT> int sum_squares(int64_t, const ValT *, double *, cudaStream_t);
 template <typename ValT> int inv_sqrt(const double *, ValT *, cudaStream_t);
+template <typename ValT>
+int norm_exchange(int64_t, const ValT *, int, int, uint64_t, double *, void *const *, void *, double *, ValT *,
+                  int *, cudaStream_t);
 }  // namespace spmvb200
 
 extern "C" {
@@ -358,6 +361,23 @@ int spmvb200_sum_squares(int value_bits, int64_t n, const void *v, double *sumsq
     if (value_bits == 64) return sum_squares<double>(n, static_cast<const double *>(v), sumsq_dev, s);
     return SPMVB200_ERR_UNSUPPORTED;
 }
+int spmvb200_norm_exchange(int value_bits, int64_t n, const void *y_local, int rank, int world,
+                           uint64_t step, void *mailbox_local, void *const *mailbox_of_rank,
+                           void *mailbox_multicast, double *sumsq_dev, void *alpha_dev, int *error_dev,
+                           spmvb200_stream_t stream) {
+    if (n < 0 || (n > 0 && !y_local)) return SPMVB200_ERR_INVALID;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (value_bits == 32)
+        return norm_exchange<float>(n, static_cast<const float *>(y_local), rank, world, step,
+                                    static_cast<double *>(mailbox_local), mailbox_of_rank, mailbox_multicast,
+                                    sumsq_dev, static_cast<float *>(alpha_dev), error_dev, s);
+    if (value_bits == 64)
+        return norm_exchange<double>(n, static_cast<const double *>(y_local), rank, world, step,
+                                     static_cast<double *>(mailbox_local), mailbox_of_rank, mailbox_multicast,
+                                     sumsq_dev, static_cast<double *>(alpha_dev), error_dev, s);
+    return SPMVB200_ERR_UNSUPPORTED;
+}
+
 int spmvb200_inv_sqrt(int value_bits, const double *sumsq_dev, void *alpha_dev, spmvb200_stream_t stream) {
     if (!sumsq_dev || !alpha_dev) return SPMVB200_ERR_INVALID;
     cudaStream_t s = static_cast<cudaStream_t>(stream);

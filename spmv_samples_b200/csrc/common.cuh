@@ -58,7 +58,7 @@ int apply_carveout(const void *kernel, int64_t percent);
 // Per-(device, stream) scratch that survives across calls, grown on demand.
 // Slots keep independent buffers so a kernel can hold several at once.
 enum ScratchSlot { SCRATCH_COORDS = 0, SCRATCH_CARRY_ROW, SCRATCH_CARRY_VAL, SCRATCH_COUNTER,
-                   SCRATCH_STATS, SCRATCH_MISC, SCRATCH_SPMM_X, SCRATCH_SPMM_Y, SCRATCH_XHOT, SCRATCH_NUM_SLOTS };
+                   SCRATCH_STATS, SCRATCH_MISC, SCRATCH_SPMM_X, SCRATCH_SPMM_Y, SCRATCH_XHOT, SCRATCH_NORM, SCRATCH_NUM_SLOTS };
 int scratch_get(cudaStream_t stream, ScratchSlot slot, size_t bytes, void **out);
 
 // What the last merge-path partition launched on a (device, stream) wrote, and where: lets a

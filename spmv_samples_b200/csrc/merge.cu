@@ -308,6 +308,11 @@ template <> struct LoadVals<double> {
     }
 };
 
+// a warp's total for the cross-warp fold: (sum since its last row start, that row / a flag)
+template <typename ValT> struct WarpTotal;
+template <> struct __align__(8) WarpTotal<float> { float val; int rid; };
+template <> struct __align__(16) WarpTotal<double> { double val; int rid; int pad; };
+
 // HOT: Aj is the remapped copy of a hot-x plan (hotx.cu): an index with the top bit set is a rank
 // into the dense copy of the hot columns' x; x_hot_biased = x_hot - 2^31 elements, so that either
 // base + (uint32) index is the address.
@@ -327,8 +332,7 @@ merge_tile_reg_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
     // 256-thread CTA and fits one more CTA per SM inside the 64 KB carveout, but measured slower:
     // R-MAT scale 24 1146 -> 1166 us, scale 27 14.70 -> 14.93 ms.)
     __shared__ __align__(16) unsigned char s_flag[SLOTS];
-    __shared__ ValT s_wval[BLOCK / 32];
-    __shared__ int s_wflag[BLOCK / 32];
+    __shared__ WarpTotal<ValT> s_w[BLOCK / 32];
 
     const int tid = threadIdx.x;
     const int64_t tile = blockIdx.x;
@@ -407,32 +411,28 @@ merge_tile_reg_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
 #pragma unroll
     for (int k = 0; k < IPT; ++k) val = ((fbits >> (8 * k)) & 1ull) ? p[k] : val + p[k];
     const int lane = tid & 31, warp = tid >> 5;
+    // the row-start bits of the warp as one ballot: lane L's sum reaches back to lane L - d iff
+    // none of lanes L - d + 1 .. L holds a flag -- 6 shuffles per thread instead of 12
+    const unsigned fmask = __ballot_sync(0xffffffffu, flag != 0);
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const ValT pvv = __shfl_up_sync(0xffffffffu, val, d);
-        const int pf = __shfl_up_sync(0xffffffffu, flag, d);
-        if (lane >= d) {
-            if (!flag) val += pvv;
-            flag |= pf;
-        }
+        if (lane >= d && ((fmask >> (lane - d + 1)) & ((1u << d) - 1u)) == 0u) val += pvv;
     }
-    if (lane == 31) {
-        s_wval[warp] = val;
-        s_wflag[warp] = flag;
+    if (lane == 31) {   // (sum since the warp's last flag, any flag): one shared-memory word
+        s_w[warp].val = val;
+        s_w[warp].rid = fmask != 0u;
     }
     ValT ev = __shfl_up_sync(0xffffffffu, val, 1);
-    int ef = __shfl_up_sync(0xffffffffu, flag, 1);
-    if (lane == 0) {
-        ev = (ValT)0;
-        ef = 0;
-    }
+    if (lane == 0) ev = (ValT)0;
+    const bool ef = (fmask & ((1u << lane) - 1u)) != 0u;
     __syncthreads();
     ValT wv = (ValT)0;
 #pragma unroll
     for (int w = 0; w < BLOCK / 32; ++w) {
         if (w < warp) {
-            const ValT v = s_wval[w];
-            wv = s_wflag[w] ? v : wv + v;
+            const WarpTotal<ValT> t = s_w[w];
+            wv = t.rid ? t.val : wv + t.val;
         }
     }
     ValT run = ef ? ev : wv + ev;
@@ -465,6 +465,194 @@ merge_tile_reg_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
     }
 }
 
+// ------------------------------------------------------------- tile kernel, marker form
+// Same tile, same loads, same products as merge_tile_reg_body, but the rows are delimited by a
+// 16-bit MARKER per slot -- the number (relative to the tile's first row, plus one) of the row
+// that starts there -- instead of a byte flag.  The segmented scan then carries the row number
+// along with the running sum, and a thread that walks over a marker knows which row has just
+// ended and with what total: it drops it into s_y[row] there and then.  What this removes from
+// the flag form (profiles/r1_merge_c5_v4: short_scoreboard + mio_throttle + barrier cost more
+// issue time than the memory latency):
+//   * the scan values are never written back to shared memory (two 128-bit stores per thread),
+//     and nobody reads Ap a second time to pick a row's total out of them;
+//   * the row-start bits of a warp travel as one ballot, so the shuffle scan moves 6 values per
+//     thread instead of 12;
+//   * (value, row) of a warp's total is one 8-byte shared-memory word: half the loads of the
+//     cross-warp fold;
+//   * the rows a warp completes are consecutive, so the warp stores them itself after a
+//     __syncwarp: three CTA barriers per tile instead of four.
+// Row r of the tile is written to y by exactly one thread: the one that holds the marker of the
+// next non-empty row (its total), or -- if r has no nonzeros at all -- the thread that set the
+// markers (0).  Summation order inside a row is unchanged (thread-serial, then lanes, then warps).
+
+template <int BLOCK, bool HAS_PEERS, bool HOT, typename OffT, typename ValT>
+__device__ __forceinline__ void
+merge_tile_mark_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
+                     const int32_t *__restrict__ Aj, const ValT *__restrict__ Ax,
+                     const ValT *__restrict__ x, ValT *__restrict__ y,
+                     const ValT *__restrict__ alpha_dev, const PeerOut &peers,
+                     const int32_t *__restrict__ coords_x, int32_t *__restrict__ carry_row,
+                     ValT *__restrict__ carry_val, const ValT *__restrict__ x_hot_biased) {
+    constexpr int IPT = kMergeIPT;
+    constexpr int SLOTS = BLOCK * IPT;
+    constexpr int TILE = SLOTS - 4;
+    static_assert(TILE < 65535, "row numbers are 16-bit markers");
+    __shared__ __align__(16) ValT s_y[SLOTS];                // totals of the rows that end in the tile
+    __shared__ __align__(16) unsigned short s_mark[SLOTS];   // slot -> 1 + row starting there, 0 = none
+    __shared__ WarpTotal<ValT> s_w[BLOCK / 32];
+
+    const int tid = threadIdx.x;
+    const int64_t tile = blockIdx.x;
+    const int64_t total = (int64_t)n_rows + (int64_t)nnz;
+    const int64_t d0 = tile * TILE;
+    const int64_t d1 = d0 + TILE < total ? d0 + TILE : total;
+    const int32_t sx = __ldg(coords_x + tile);
+    const int32_t ex = __ldg(coords_x + tile + 1);
+    const int64_t sy = d0 - sx;
+    const int R = ex - sx;
+    const int Z = (int)((d1 - ex) - sy);
+    const int shift = (int)(sy & 3);
+    const int64_t a0 = sy - shift;
+
+    *reinterpret_cast<uint4 *>(s_mark + tid * IPT) = make_uint4(0u, 0u, 0u, 0u);
+
+    const int slot0 = tid * IPT;
+    const uint64_t pol_stream = policy_evict_first();
+    const uint64_t pol_x = policy_evict_last();
+    int c[IPT];
+    ValT p[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        c[k] = 0;
+        p[k] = (ValT)0;
+    }
+    if (slot0 < shift + Z) {
+        const int64_t g = a0 + slot0;
+        if (g + IPT <= (int64_t)nnz) {
+            const int4 ca = ldg_stream_int4(Aj + g, pol_stream);
+            const int4 cb = ldg_stream_int4(Aj + g + 4, pol_stream);
+            c[0] = ca.x; c[1] = ca.y; c[2] = ca.z; c[3] = ca.w;
+            c[4] = cb.x; c[5] = cb.y; c[6] = cb.z; c[7] = cb.w;
+            LoadVals<ValT>::vec8(Ax + g, pol_stream, p);
+        } else {
+#pragma unroll
+            for (int k = 0; k < IPT; ++k) {
+                if (g + k < (int64_t)nnz) {
+                    c[k] = __ldg(Aj + g + k);
+                    p[k] = __ldg(Ax + g + k);
+                }
+            }
+        }
+    }
+    const ValT alpha = alpha_dev ? __ldg(alpha_dev) : (ValT)1;
+    __syncthreads();  // markers are clear
+
+    // ---- markers, one thread per row end j (row sx+j ends, row sx+j+1 starts at q).  Of a run of
+    // rows starting at the same position only the last has nonzeros from there on: it sets the
+    // marker; a row without nonzeros is finished here (0).
+    for (int j = tid; j < R; j += BLOCK) {
+        const OffT b = __ldg(Ap + sx + j);
+        const OffT e = __ldg(Ap + sx + 1 + j);
+        const int q = (int)((int64_t)e - sy);
+        if (j == R - 1 || __ldg(Ap + sx + 2 + j) != e) s_mark[q + shift] = (unsigned short)(j + 1);
+        if (b == e) s_y[j] = (ValT)0;
+    }
+    // ---- x gathers, all eight issued before the first use
+    {
+        ValT xv[IPT];
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+            const int i = slot0 + k - shift;
+            const ValT *src = HOT ? (c[k] < 0 ? x_hot_biased : x) + (uint32_t)c[k] : x + c[k];
+            xv[k] = (i >= 0 && i < Z) ? ldg_hint(src, pol_x) : (ValT)0;
+        }
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+            const int i = slot0 + k - shift;
+            p[k] = (i >= 0 && i < Z) ? p[k] * xv[k] : (ValT)0;
+        }
+    }
+    __syncthreads();  // markers are set
+
+    // ---- this thread's eight markers; pass 1: (sum since the last marker, last row started)
+    const uint4 mw = *reinterpret_cast<const uint4 *>(s_mark + slot0);
+    const unsigned m32[4] = {mw.x, mw.y, mw.z, mw.w};
+    int mk[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) mk[k] = (int)((m32[k >> 1] >> (16 * (k & 1))) & 0xffffu);
+    ValT val = (ValT)0;
+    int rid = 0;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        val = mk[k] ? p[k] : val + p[k];
+        rid = mk[k] ? mk[k] : rid;
+    }
+    const int lane = tid & 31, warp = tid >> 5;
+    // lanes holding a marker, as one word: lane L's sum extends back to lane L - d iff none of
+    // lanes L - d + 1 .. L holds one
+    const unsigned fmask = __ballot_sync(0xffffffffu, rid != 0);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const ValT pv = __shfl_up_sync(0xffffffffu, val, d);
+        if (lane >= d && ((fmask >> (lane - d + 1)) & ((1u << d) - 1u)) == 0u) val += pv;
+    }
+    // carry into this lane from the lanes below it: their inclusive sum, and the row they are in
+    ValT ev = __shfl_up_sync(0xffffffffu, val, 1);
+    if (lane == 0) ev = (ValT)0;
+    const unsigned below = fmask & ((1u << lane) - 1u);
+    const int src_lane = below ? 31 - __clz(below) : 0;
+    int erow = __shfl_sync(0xffffffffu, rid, src_lane);
+    if (lane == 31) {   // the warp's total: sum since its last marker, and that marker's row (0 = none)
+        s_w[warp].val = val;
+        s_w[warp].rid = rid ? rid : (below ? erow : 0);
+    }
+    __syncthreads();
+    ValT wv = (ValT)0;
+    int wrow = 0;
+#pragma unroll
+    for (int w = 0; w < BLOCK / 32; ++w) {
+        if (w < warp) {
+            const WarpTotal<ValT> t = s_w[w];
+            wv = t.rid ? t.val : wv + t.val;
+            wrow = t.rid ? t.rid : wrow;
+        }
+    }
+    // ---- pass 2: walk the slots again from the carry-in; a marker closes the current row
+    ValT run = below ? ev : wv + ev;
+    int row = below ? erow : wrow;
+    const int first_row = row;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        if (mk[k]) {
+            s_y[row] = alpha * run;
+            run = p[k];
+            row = mk[k];
+        } else {
+            run += p[k];
+        }
+    }
+    // ---- the rows this warp completed are consecutive: [row entering lane 0, row leaving lane 31)
+    __syncwarp();
+    const int r_begin = __shfl_sync(0xffffffffu, first_row, 0);
+    const int r_end = __shfl_sync(0xffffffffu, row, 31);
+    for (int j = r_begin + lane; j < r_end; j += 32) {
+        const ValT v = s_y[j];
+        if (HAS_PEERS) {
+            // peers only get rows with nonzeros in this tile (see store_y_nonempty)
+            const int64_t b64 = (int64_t)__ldg(Ap + sx + j) - sy;
+            const int64_t q64 = (int64_t)__ldg(Ap + sx + 1 + j) - sy;
+            store_y_nonempty(y, peers, (int64_t)sx + j, v, q64 > (b64 > 0 ? b64 : 0));
+        } else {
+            y[(int64_t)sx + j] = v;
+        }
+    }
+    if (tid == BLOCK - 1) {
+        // what follows the last row end belongs to row ex: carry it out
+        carry_row[tile] = sx + row;
+        carry_val[tile] = run;
+    }
+}
+
 // Two entry points over one body, because the register budget is set per __global__: with
 // 32-bit offsets and fp32 the body fits 32 registers without spilling (8 CTAs/SM; c3 1328 ->
 // 1230 us); the 64-bit-offset and fp64 bodies spill under that cap and are left to ptxas
@@ -474,22 +662,38 @@ merge_tile_reg_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
     const ValT *__restrict__ Ax, const ValT *__restrict__ x, ValT *__restrict__ y,               \
     const ValT *__restrict__ alpha_dev, PeerOut peers, const int32_t *__restrict__ coords_x,     \
     int32_t *__restrict__ carry_row, ValT *__restrict__ carry_val
-template <int BLOCK, bool HAS_PEERS, typename OffT, typename ValT>
-__global__ void __launch_bounds__(BLOCK, 2048 / BLOCK) merge_tile_reg_kernel_occ8(MERGE_REG_KERNEL_ARGS) {
-    merge_tile_reg_body<BLOCK, HAS_PEERS, false, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers,
-                                                             coords_x, carry_row, carry_val, nullptr);
+// ALGO 0 = marker form (the default), 1 = the flag form of round 1 (option "merge_algo", A/B)
+template <int ALGO, int BLOCK, bool HAS_PEERS, bool HOT, typename OffT, typename ValT>
+__device__ __forceinline__ void merge_tile_dispatch(MERGE_REG_KERNEL_ARGS, const ValT *__restrict__ x_hot_biased) {
+    if (ALGO == 0)
+        merge_tile_mark_body<BLOCK, HAS_PEERS, HOT, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers,
+                                                                coords_x, carry_row, carry_val, x_hot_biased);
+    else
+        merge_tile_reg_body<BLOCK, HAS_PEERS, HOT, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers,
+                                                               coords_x, carry_row, carry_val, x_hot_biased);
 }
-template <int BLOCK, bool HAS_PEERS, typename OffT, typename ValT>
+template <int ALGO, int BLOCK, bool HAS_PEERS, typename OffT, typename ValT>
+__global__ void __launch_bounds__(BLOCK, 2048 / BLOCK) merge_tile_reg_kernel_occ8(MERGE_REG_KERNEL_ARGS) {
+    merge_tile_dispatch<ALGO, BLOCK, HAS_PEERS, false, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers,
+                                                                   coords_x, carry_row, carry_val, nullptr);
+}
+template <int ALGO, int BLOCK, bool HAS_PEERS, typename OffT, typename ValT>
 __global__ void __launch_bounds__(BLOCK) merge_tile_reg_kernel(MERGE_REG_KERNEL_ARGS) {
-    merge_tile_reg_body<BLOCK, HAS_PEERS, false, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers,
-                                                             coords_x, carry_row, carry_val, nullptr);
+    merge_tile_dispatch<ALGO, BLOCK, HAS_PEERS, false, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers,
+                                                                   coords_x, carry_row, carry_val, nullptr);
 }
 // the hot-x variant: Aj is the plan's remapped copy
-template <int BLOCK, bool HAS_PEERS, typename OffT, typename ValT>
+template <int ALGO, int BLOCK, bool HAS_PEERS, typename OffT, typename ValT>
+__global__ void __launch_bounds__(BLOCK, 2048 / BLOCK)
+merge_tile_hot_kernel_occ8(MERGE_REG_KERNEL_ARGS, const ValT *__restrict__ x_hot_biased) {
+    merge_tile_dispatch<ALGO, BLOCK, HAS_PEERS, true, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers,
+                                                                  coords_x, carry_row, carry_val, x_hot_biased);
+}
+template <int ALGO, int BLOCK, bool HAS_PEERS, typename OffT, typename ValT>
 __global__ void __launch_bounds__(BLOCK)
 merge_tile_hot_kernel(MERGE_REG_KERNEL_ARGS, const ValT *__restrict__ x_hot_biased) {
-    merge_tile_reg_body<BLOCK, HAS_PEERS, true, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers,
-                                                            coords_x, carry_row, carry_val, x_hot_biased);
+    merge_tile_dispatch<ALGO, BLOCK, HAS_PEERS, true, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers,
+                                                                  coords_x, carry_row, carry_val, x_hot_biased);
 }
 #undef MERGE_REG_KERNEL_ARGS
 
@@ -851,10 +1055,17 @@ int launch_merge(const SpmvProblem<OffT, ValT> &p) {
                                          (const int32_t *)coords, static_cast<int32_t *>(crow),
                                          static_cast<ValT *>(cval)));
     } else {
-        // (o32, fp32) needs the explicit occupancy bound to stay at 32 registers; (o64, fp32)
-        // gets 32 registers from ptxas unprompted and spills under the bound; fp64 needs 64
-        constexpr bool occ = sizeof(ValT) == 4 && sizeof(OffT) == 4;
         const bool has_peers = p.peers.n != 0;
+        // tile body: "merge_algo" 0 = row markers, 1 = byte flags, -1 (default) by value type.
+        // Measured (L2 flushed): fp32 flags 1121 us / markers 1140 us on R-MAT scale 24 (the marker
+        // form costs 8 more registers and 2 KB more shared memory per CTA), fp64 746 / 683 us on the
+        // 65536 x 2048 matrix (no second pass over Ap, one barrier less).
+        const int64_t algo_opt = option_get("merge_algo", -1);
+        const bool flags_form = algo_opt < 0 ? sizeof(ValT) == 4 : algo_opt == 1;
+        // 8 CTAs of 256 threads per SM need 32 registers: the bound is only applied where ptxas meets
+        // it without spilling (fp32: both forms with 32-bit offsets, the marker form with 64-bit;
+        // fp64 needs 48-64 registers either way)
+        const bool occ = sizeof(ValT) == 4 && (sizeof(OffT) == 4 || !flags_form);
         // hot-x plan (hotx.cu): by default only for a caller that vouches for an unchanged matrix
         // and an x far longer than the TLB and the L2 reach
         const int64_t hot_opt = option_get("hot_x", -1);
@@ -870,8 +1081,11 @@ int launch_merge(const SpmvProblem<OffT, ValT> &p) {
         if (hot) {
             const ValT *x_hot = nullptr;
             SPMV_TRY(hot_gather<ValT>(*hot, p.x, p.stream, &x_hot));
-            auto kernel = has_peers ? merge_tile_hot_kernel<RB, true, OffT, ValT>
-                                    : merge_tile_hot_kernel<RB, false, OffT, ValT>;
+            auto kernel = flags_form ? (has_peers ? merge_tile_hot_kernel<1, RB, true, OffT, ValT>
+                                                  : merge_tile_hot_kernel<1, RB, false, OffT, ValT>)
+                                     : (has_peers ? merge_tile_hot_kernel<0, RB, true, OffT, ValT>
+                                        : occ     ? merge_tile_hot_kernel_occ8<0, RB, false, OffT, ValT>
+                                                  : merge_tile_hot_kernel<0, RB, false, OffT, ValT>);
             SPMV_TRY(apply_carveout(reinterpret_cast<const void *>(kernel), carveout));
             const ValT *x_hot_biased = x_hot - ((ptrdiff_t)1 << 31);
             KernelTimerScope timed(p.stream);
@@ -880,9 +1094,12 @@ int launch_merge(const SpmvProblem<OffT, ValT> &p) {
                                              static_cast<int32_t *>(crow), static_cast<ValT *>(cval),
                                              x_hot_biased));
         } else {
-            auto kernel = has_peers ? merge_tile_reg_kernel<RB, true, OffT, ValT>      // 40 regs, no spill
-                          : occ     ? merge_tile_reg_kernel_occ8<RB, false, OffT, ValT>
-                                    : merge_tile_reg_kernel<RB, false, OffT, ValT>;
+            auto kernel = flags_form ? (has_peers ? merge_tile_reg_kernel<1, RB, true, OffT, ValT>   // 40 regs, no spill
+                                        : occ     ? merge_tile_reg_kernel_occ8<1, RB, false, OffT, ValT>
+                                                  : merge_tile_reg_kernel<1, RB, false, OffT, ValT>)
+                                     : (has_peers ? merge_tile_reg_kernel<0, RB, true, OffT, ValT>
+                                        : occ     ? merge_tile_reg_kernel_occ8<0, RB, false, OffT, ValT>
+                                                  : merge_tile_reg_kernel<0, RB, false, OffT, ValT>);
             SPMV_TRY(apply_carveout(reinterpret_cast<const void *>(kernel), carveout));
             KernelTimerScope timed(p.stream);
             SPMV_CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, kernel, p.n_rows, p.nnz, p.Ap, p.Aj, p.Ax, p.x, p.y,

@@ -52,6 +52,7 @@ std::map<std::string, int64_t> &options() {
         {"cusparse_preprocess", 0},  // 1: run cusparseSpMV_preprocess when a plan is built.  Only
                                      // safe while the matrix contents behind (Ap, Aj, Ax) do not
                                      // change; bench.py turns it on for the baseline timing
+        {"merge_algo", -1},      // tile body of the merge-path kernel: 0 = row markers, 1 = byte flags, -1 = by value type
         {"hot_x", -1},           // compacted hot part of x in the merge-path kernel: -1 = when the caller
                                  // passes SPMVB200_FLAG_STATIC_PATTERN and x is longer than
                                  // "hot_x_min_bytes"; 0 = never; 1 = always (plan keyed on the Aj pointer)
@@ -109,6 +110,8 @@ int scratch_get(cudaStream_t stream, ScratchSlot slot, size_t bytes, void **out)
         size_t want = bytes + bytes / 4;
         void *np = nullptr;
         SPMV_CUDA_TRY(cudaMalloc(&np, want));
+        // new scratch starts zeroed (the block counter of the norm exchange relies on it)
+        SPMV_CUDA_TRY(cudaMemsetAsync(np, 0, want, stream));
         if (b.ptr) {
             SPMV_CUDA_TRY(cudaStreamSynchronize(stream));
             SPMV_CUDA_TRY(cudaFree(b.ptr));

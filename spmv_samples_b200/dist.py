@@ -36,6 +36,8 @@ import torch
 
 from . import _lib, generate, spmv as spmv_mod
 
+MAILBOX_BYTES = 256   # SPMVB200_MAILBOX_BYTES in include/spmv_b200.h
+
 
 class _RawDeviceArray:
     """A cudaMalloc'ed buffer exposed to torch without copying (__cuda_array_interface__)."""
@@ -150,6 +152,13 @@ class PowerIteration:
         self._raw, self._symm = [], []
         self.peer_ptrs = [[], []]   # per buffer: peers' base addresses mapped into this process
         self.mc_ptrs = [0, 0]       # per buffer: NVLink multicast address (exchange "mc")
+        # Every replica of x is allocated with a small tail: buffer 0's holds this rank's mailbox
+        # of the norm exchange (csrc/power.cu), so whatever maps the replicas into the peers --
+        # cudaIpc, symmetric memory, multicast -- maps the mailboxes too.
+        item = torch.empty(0, dtype=self.dtype).element_size()
+        self._tail_off = (self.n * item + 255) // 256 * 256
+        self._alloc_elems = (self._tail_off + MAILBOX_BYTES + item - 1) // item
+        self._xchg_step = 0         # never reset: the mailbox slots are addressed by it
         if host_ops is None:
             if not torch.cuda.is_available():
                 raise RuntimeError("PowerIteration needs a CUDA device; there is no CPU path")
@@ -165,10 +174,11 @@ class PowerIteration:
                 except Exception as e:  # no symmetric memory / no NVLS here
                     self.exchange_note = f"multicast unavailable ({type(e).__name__}: {e}); "
                     self.exchange = "p2p"
-                    self._symm, self.xbuf = [], []
+                    self._symm, self.xbuf, self._full = [], [], []
             if self.exchange != "mc":
-                self._raw = [_RawDeviceArray(self.n, self.dtype) for _ in range(2)]
-                self.xbuf = [r.tensor() for r in self._raw]
+                self._raw = [_RawDeviceArray(self._alloc_elems, self.dtype) for _ in range(2)]
+                self._full = [r.tensor() for r in self._raw]
+                self.xbuf = [t[:self.n] for t in self._full]
             if self.exchange == "p2p":
                 try:
                     self._map_peers()
@@ -184,6 +194,11 @@ class PowerIteration:
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
         self.alpha = torch.ones(1, dtype=self.dtype, device=dev)
         self.step_no = 0
+        # the norm exchange kernel replaces sum of squares + all-reduce + 1/sqrt wherever the
+        # mailboxes are mapped into the peers (always on one GPU); "nccl" keeps the collective
+        self.fused_norm = host_ops is None and self.exchange in ("none", "p2p", "mc")
+        if self.fused_norm:
+            self._init_mailbox()
         self.reset()
 
     # ------------------------------------------------------------------ setup
@@ -194,8 +209,9 @@ class PowerIteration:
         import torch.distributed._symmetric_memory as symm_mem
         group = self.group if self.group is not None else self.dist.group.WORLD
         dev = torch.device("cuda", torch.cuda.current_device())
-        self.xbuf = [symm_mem.empty(self.n, dtype=self.dtype, device=dev) for _ in range(2)]
-        for t in self.xbuf:
+        self._full = [symm_mem.empty(self._alloc_elems, dtype=self.dtype, device=dev) for _ in range(2)]
+        self.xbuf = [t[:self.n] for t in self._full]
+        for t in self._full:
             try:
                 h = symm_mem.rendezvous(t, group.group_name)
             except TypeError:
@@ -206,6 +222,28 @@ class PowerIteration:
         self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN, group=self.group)
         if int(ok.item()) == 0:
             raise RuntimeError("no multicast pointer")
+
+    def _init_mailbox(self):
+        """Mailbox of the norm exchange in the tail of replica 0: all slots empty (-1.0), and the
+        addresses under which every rank's mailbox is reached from here."""
+        base = self._full[0].data_ptr()
+        self._mailbox = base + self._tail_off
+        tail = self._full[0].view(torch.uint8)[self._tail_off:self._tail_off + MAILBOX_BYTES]
+        tail.view(torch.float64).fill_(-1.0)
+        self.xchg_error = torch.zeros(1, dtype=torch.int32, device="cuda")
+        self._mailbox_mc = 0
+        ptrs = [0] * self.world
+        ptrs[self.rank] = self._mailbox
+        if self.exchange == "mc":
+            self._mailbox_mc = self.mc_ptrs[0] + self._tail_off
+        elif self.exchange == "p2p":
+            others = [q for q in range(self.world) if q != self.rank]
+            for q, p in zip(others, self.peer_ptrs[0]):
+                ptrs[q] = p + self._tail_off
+        self._mailbox_of_rank = (C.c_void_p * self.world)(*ptrs)
+        torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier(group=self.group)   # every mailbox is empty before anybody publishes
 
     def _map_peers(self):
         handles = [r.ipc_handle() for r in self._raw]
@@ -260,6 +298,16 @@ class PowerIteration:
                 # and before the step barrier lets any peer store into it.
                 self.xbuf[0].zero_()
             L = _lib.lib()
+            if self.fused_norm and self._local_events is None:
+                # sum of squares, exchange of the per-rank sums, alpha and the step barrier: one kernel
+                st = L.spmvb200_norm_exchange(
+                    self.vbits, y.numel(), y.data_ptr(), self.rank, self.world, self._xchg_step,
+                    self._mailbox, self._mailbox_of_rank, self._mailbox_mc or None, self.sumsq.data_ptr(),
+                    self.alpha.data_ptr(), self.xchg_error.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                _lib.check(st, "spmvb200_norm_exchange")
+                self._xchg_step += 1
+                self.step_no += 1
+                return
             st = L.spmvb200_sum_squares(self.vbits, y.numel(), y.data_ptr(), self.sumsq.data_ptr(),
                                         torch.cuda.current_stream().cuda_stream)
             _lib.check(st, "spmvb200_sum_squares")
@@ -329,13 +377,22 @@ class PowerIteration:
         """The latest iterate, not yet scaled by alpha (= 1 / its norm)."""
         return self.xbuf[self.step_no & 1]
 
+    def check_exchange(self):
+        """Raise if a rank failed to arrive at a norm exchange (the kernel gives up after ~4 s)."""
+        if getattr(self, "fused_norm", False):
+            e = int(self.xchg_error.item())
+            if e:
+                raise RuntimeError(f"norm exchange: rank {e - 1} did not arrive within the time limit")
+
     def eigen_estimate(self) -> float:
         """||A x_k|| with ||x_k|| = 1: converges to |lambda_max|."""
+        self.check_exchange()
         return float(self.sumsq.item()) ** 0.5
 
     def close(self):
         if self.host_ops is None:
             torch.cuda.synchronize()
+            self.check_exchange()
         if self.world > 1:
             self.dist.barrier(group=self.group)
         for b in range(2):
@@ -343,6 +400,7 @@ class PowerIteration:
                 _lib.lib().spmvb200_ipc_close(C.c_void_p(p))
         self.peer_ptrs = [[], []]
         self.xbuf = []
+        self._full = []
         self._symm = []
         for r in self._raw:
             r.free()

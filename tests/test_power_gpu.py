@@ -285,3 +285,112 @@ def test_pipelined_host_buffer_api_matches_serial(slots):
     with pytest.raises(ValueError):
         mat.spmv_many(xs, ys, slots=5)
     mat.close()
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_norm_exchange_single_rank(dt):
+    """The fused norm kernel with world = 1: sum of squares (deterministic), alpha, slot rotation
+    over many steps, the block counter resetting itself, no error raised."""
+    from spmv_samples_b200 import _lib
+    L = _lib.lib()
+    bits = 32 if dt == np.float32 else 64
+    mailbox = torch.full((_lib_mailbox_doubles(),), -1.0, dtype=torch.float64, device="cuda")
+    ss = torch.zeros(1, dtype=torch.float64, device="cuda")
+    alpha = torch.zeros(1, dtype=torch.float32 if dt == np.float32 else torch.float64, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ptrs = (C.c_void_p * 1)(mailbox.data_ptr())
+    s = torch.cuda.current_stream().cuda_stream
+    seen = []
+    for step in range(7):
+        v = g.gen_x(30 + step, 300_007 + 1000 * step, dt)
+        d = dev(v)
+        _lib.check(L.spmvb200_norm_exchange(bits, d.numel(), d.data_ptr(), 0, 1, step, mailbox.data_ptr(),
+                                            ptrs, None, ss.data_ptr(), alpha.data_ptr(), err.data_ptr(), s),
+                   "norm_exchange")
+        torch.cuda.synchronize()
+        expect = float((v.astype(np.float64) ** 2).sum())
+        assert abs(float(ss.item()) - expect) <= 1e-12 * expect
+        assert abs(float(alpha.item()) - expect ** -0.5) <= 1e-6 * expect ** -0.5
+        seen.append(float(ss.item()))
+    assert int(err.item()) == 0
+    # same input, same bits
+    v = g.gen_x(30, 300_007, dt)
+    d = dev(v)
+    _lib.check(L.spmvb200_norm_exchange(bits, d.numel(), d.data_ptr(), 0, 1, 7, mailbox.data_ptr(), ptrs, None,
+                                        ss.data_ptr(), alpha.data_ptr(), err.data_ptr(), s), "norm_exchange")
+    torch.cuda.synchronize()
+    assert float(ss.item()) == seen[0]
+
+
+def _lib_mailbox_doubles():
+    from spmv_samples_b200.dist import MAILBOX_BYTES
+    return MAILBOX_BYTES // 8
+
+
+# ------------------------------------------------------------------ one process, N GPUs (csrc/multi.cu)
+def _native_power(n_gpus, Ap, Aj, Ax, steps, from_device=False, kind=3):
+    from spmv_samples_b200 import _lib
+    L = _lib.lib()
+    n = Ap.shape[0] - 1
+    h = C.c_void_p()
+    ob, vb = Ap.dtype.itemsize * 8, Ax.dtype.itemsize * 8
+    if from_device:
+        dAp, dAj, dAx = dev(Ap), dev(Aj), dev(Ax)
+        st = L.spmvb200_power_create_from_device(n_gpus, None, ob, vb, n, Aj.size, dAp.data_ptr(), dAj.data_ptr(),
+                                                 dAx.data_ptr(), kind, C.byref(h))
+    else:
+        st = L.spmvb200_power_create(n_gpus, None, ob, vb, n, Aj.size, Ap.ctypes.data, Aj.ctypes.data,
+                                     Ax.ctypes.data, kind, C.byref(h))
+    _lib.check(st, "spmvb200_power_create")
+    try:
+        ms = C.c_double()
+        _lib.check(L.spmvb200_power_run(h, steps, C.byref(ms)), "spmvb200_power_run")
+        x = np.empty(n, dtype=Ax.dtype)
+        norm = C.c_double()
+        rb = (C.c_int64 * (n_gpus + 1))()
+        _lib.check(L.spmvb200_power_get(h, x.ctypes.data, C.byref(norm), rb), "spmvb200_power_get")
+        # a second run after reset reproduces the first bit for bit
+        _lib.check(L.spmvb200_power_reset(h), "spmvb200_power_reset")
+        _lib.check(L.spmvb200_power_steps(h, steps), "spmvb200_power_steps")
+        x2 = np.empty(n, dtype=Ax.dtype)
+        _lib.check(L.spmvb200_power_get(h, x2.ctypes.data, None, None), "spmvb200_power_get")
+    finally:
+        L.spmvb200_power_destroy(h)
+    assert np.array_equal(x, x2)
+    return x, norm.value, list(rb), ms.value
+
+
+def _oracle_power(Ap, Aj, Ax, steps):
+    n = Ap.shape[0] - 1
+    x = np.full(n, 1.0 / np.sqrt(n), dtype=np.float64)
+    alpha = 1.0
+    for _ in range(steps):
+        y = cpu.spmv_fp64(Ap, Aj, Ax, x.astype(Ax.dtype)) * alpha
+        alpha = 1.0 / np.sqrt((y ** 2).sum())
+        x = y
+    return x
+
+
+@pytest.mark.parametrize("from_device", [False, True])
+@pytest.mark.parametrize("off", [np.int32, np.int64])
+def test_native_power_iteration_one_gpu(off, from_device):
+    Ap, Aj, Ax = g.rmat(12, 16, 7, offset_dtype=off)
+    x, norm, rb, ms = _native_power(1, Ap, Aj, Ax, 8, from_device)
+    ref = _oracle_power(Ap, Aj, Ax, 8)
+    assert np.linalg.norm(x.astype(np.float64) - ref) <= 1e-4 * np.linalg.norm(ref)
+    assert abs(norm - np.sqrt((ref ** 2).sum())) <= 1e-4 * norm
+    assert rb == [0, Ap.shape[0] - 1] and ms > 0
+
+
+@pytest.mark.parametrize("n_gpus", [2, 4, 8])
+def test_native_power_iteration_multi_gpu(n_gpus):
+    """Row blocks on n_gpus GPUs of this process, fused peer-store exchange, mailbox norm exchange:
+    same iterates as the oracle recurrence, row split bit-exact against the oracle's merge path."""
+    if torch.cuda.device_count() < n_gpus:
+        pytest.skip(f"needs {n_gpus} GPUs")
+    Ap, Aj, Ax = g.rmat(14, 16, 7, offset_dtype=np.int64)
+    x, norm, rb, ms = _native_power(n_gpus, Ap, Aj, Ax, 6)
+    assert rb == cpu.row_split(Ap, n_gpus).tolist()
+    ref = _oracle_power(Ap, Aj, Ax, 6)
+    assert np.linalg.norm(x.astype(np.float64) - ref) <= 1e-4 * np.linalg.norm(ref)
+    assert abs(norm - np.sqrt((ref ** 2).sum())) <= 1e-4 * norm
