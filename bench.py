@@ -459,7 +459,7 @@ def configs_leg(peak, iters=15):
         # "stream" gives a row to a thread: only timed on the matrices it is meant for (a hub row
         # of R-MAT scale 24 keeps one thread busy for a second)
         kinds = ["merge", "vector", "light", "auto"]
-        if st["mean_row_len"] <= 8.0 and st["max_row_len"] <= 64:
+        if st["mean_row_len"] <= 8.0 and st["max_row_len"] <= 64:   # wider than the selector's own rule (<= 6)
             kinds.insert(3, "stream")
         for k in kinds:
             for _ in range(3):

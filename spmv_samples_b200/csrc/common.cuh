@@ -143,7 +143,10 @@ int launch_spmm(int k, int32_t n_rows, int32_t n_cols, OffT nnz, const OffT *Ap,
 struct HotPlan {
     const int32_t *Aj2 = nullptr;
     const int32_t *hot_cols = nullptr;
+    const uint32_t *bitmap = nullptr;   // bit c % 32 of word c / 32: column c is hot
+    const uint32_t *rank32 = nullptr;   // rank of the first hot column of each word
     int64_t K = 0;
+    int32_t n_cols = 0;
     uint32_t threshold = 0;   // a column is hot when it occurs at least this often
     double hot_share = 0.0;   // fraction of the gathers that go to hot columns
     double build_ms = 0.0;
@@ -160,7 +163,7 @@ int gather_yardstick(int64_t n_x, int64_t count, int reps, cudaStream_t stream, 
 // Launch attribute helper: optional L2 access-policy window over x (option "l2_window").
 struct LaunchCfg {
     cudaLaunchConfig_t cfg;
-    cudaLaunchAttribute attrs[2];
+    cudaLaunchAttribute attrs[3];
 };
 void make_launch_cfg(LaunchCfg &lc, dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                      const void *x, size_t x_bytes);

@@ -316,7 +316,7 @@ template <> struct __align__(16) WarpTotal<double> { double val; int rid; int pa
 // HOT: Aj is the remapped copy of a hot-x plan (hotx.cu): an index with the top bit set is a rank
 // into the dense copy of the hot columns' x; x_hot_biased = x_hot - 2^31 elements, so that either
 // base + (uint32) index is the address.
-template <int BLOCK, bool HAS_PEERS, bool HOT, typename OffT, typename ValT>
+template <int BLOCK, int HAS_PEERS, bool HOT, typename OffT, typename ValT>
 __device__ __forceinline__ void
 merge_tile_reg_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
                     const int32_t *__restrict__ Aj, const ValT *__restrict__ Ax,
@@ -334,6 +334,11 @@ merge_tile_reg_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
     __shared__ __align__(16) unsigned char s_flag[SLOTS];
     __shared__ WarpTotal<ValT> s_w[BLOCK / 32];
 
+    // The hot-x kernel is launched with programmatic stream serialization right behind the small
+    // kernel that refills x_hot: it may be set up -- and its CTAs may arrive here -- while that
+    // kernel still runs; nothing is read before it has completed.  (Launched the ordinary way the
+    // GPU sat idle ~160 us between the two on R-MAT scale 27, profiles/r2_step_kernels.txt.)
+    if (HOT) asm volatile("griddepcontrol.wait;" ::: "memory");
     const int tid = threadIdx.x;
     const int64_t tile = blockIdx.x;
     const int64_t total = (int64_t)n_rows + (int64_t)nnz;
@@ -454,8 +459,16 @@ merge_tile_reg_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
         const ValT sum = q > b ? scan[q - 1] : (ValT)0;
         // the peer fan-out is compiled in only when there are peers: its code cost the
         // (o32, fp32) kernel its 32-register budget (spills; c3 1224 -> 1459 us)
-        if (HAS_PEERS) store_y_nonempty(y, peers, (int64_t)sx + j, alpha * sum, q > b);
-        else y[(int64_t)sx + j] = alpha * sum;
+        // HAS_PEERS 2: the peers are one NVLink multicast address -- a single pointer instead of the
+        // list keeps the kernel inside 32 registers (the list costs 8 more and two CTAs per SM)
+        if (HAS_PEERS == 2) {
+            y[(int64_t)sx + j] = alpha * sum;
+            if (q > b) multimem_st(static_cast<ValT *>(peers.ptr[0]) + (int64_t)sx + j, alpha * sum);
+        } else if (HAS_PEERS) {
+            store_y_nonempty(y, peers, (int64_t)sx + j, alpha * sum, q > b);
+        } else {
+            y[(int64_t)sx + j] = alpha * sum;
+        }
     }
     if (tid == 0) {
         const int64_t lq = R > 0 ? (int64_t)__ldg(Ap + ex) - sy : 0;
@@ -485,7 +498,7 @@ merge_tile_reg_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
 // next non-empty row (its total), or -- if r has no nonzeros at all -- the thread that set the
 // markers (0).  Summation order inside a row is unchanged (thread-serial, then lanes, then warps).
 
-template <int BLOCK, bool HAS_PEERS, bool HOT, typename OffT, typename ValT>
+template <int BLOCK, int HAS_PEERS, bool HOT, typename OffT, typename ValT>
 __device__ __forceinline__ void
 merge_tile_mark_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
                      const int32_t *__restrict__ Aj, const ValT *__restrict__ Ax,
@@ -501,6 +514,11 @@ merge_tile_mark_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
     __shared__ __align__(16) unsigned short s_mark[SLOTS];   // slot -> 1 + row starting there, 0 = none
     __shared__ WarpTotal<ValT> s_w[BLOCK / 32];
 
+    // The hot-x kernel is launched with programmatic stream serialization right behind the small
+    // kernel that refills x_hot: it may be set up -- and its CTAs may arrive here -- while that
+    // kernel still runs; nothing is read before it has completed.  (Launched the ordinary way the
+    // GPU sat idle ~160 us between the two on R-MAT scale 27, profiles/r2_step_kernels.txt.)
+    if (HOT) asm volatile("griddepcontrol.wait;" ::: "memory");
     const int tid = threadIdx.x;
     const int64_t tile = blockIdx.x;
     const int64_t total = (int64_t)n_rows + (int64_t)nnz;
@@ -641,7 +659,13 @@ merge_tile_mark_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
             // peers only get rows with nonzeros in this tile (see store_y_nonempty)
             const int64_t b64 = (int64_t)__ldg(Ap + sx + j) - sy;
             const int64_t q64 = (int64_t)__ldg(Ap + sx + 1 + j) - sy;
-            store_y_nonempty(y, peers, (int64_t)sx + j, v, q64 > (b64 > 0 ? b64 : 0));
+            const bool has = q64 > (b64 > 0 ? b64 : 0);
+            if (HAS_PEERS == 2) {
+                y[(int64_t)sx + j] = v;
+                if (has) multimem_st(static_cast<ValT *>(peers.ptr[0]) + (int64_t)sx + j, v);
+            } else {
+                store_y_nonempty(y, peers, (int64_t)sx + j, v, has);
+            }
         } else {
             y[(int64_t)sx + j] = v;
         }
@@ -663,7 +687,7 @@ merge_tile_mark_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
     const ValT *__restrict__ alpha_dev, PeerOut peers, const int32_t *__restrict__ coords_x,     \
     int32_t *__restrict__ carry_row, ValT *__restrict__ carry_val
 // ALGO 0 = marker form (the default), 1 = the flag form of round 1 (option "merge_algo", A/B)
-template <int ALGO, int BLOCK, bool HAS_PEERS, bool HOT, typename OffT, typename ValT>
+template <int ALGO, int BLOCK, int HAS_PEERS, bool HOT, typename OffT, typename ValT>
 __device__ __forceinline__ void merge_tile_dispatch(MERGE_REG_KERNEL_ARGS, const ValT *__restrict__ x_hot_biased) {
     if (ALGO == 0)
         merge_tile_mark_body<BLOCK, HAS_PEERS, HOT, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers,
@@ -672,24 +696,24 @@ __device__ __forceinline__ void merge_tile_dispatch(MERGE_REG_KERNEL_ARGS, const
         merge_tile_reg_body<BLOCK, HAS_PEERS, HOT, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers,
                                                                coords_x, carry_row, carry_val, x_hot_biased);
 }
-template <int ALGO, int BLOCK, bool HAS_PEERS, typename OffT, typename ValT>
+template <int ALGO, int BLOCK, int HAS_PEERS, typename OffT, typename ValT>
 __global__ void __launch_bounds__(BLOCK, 2048 / BLOCK) merge_tile_reg_kernel_occ8(MERGE_REG_KERNEL_ARGS) {
     merge_tile_dispatch<ALGO, BLOCK, HAS_PEERS, false, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers,
                                                                    coords_x, carry_row, carry_val, nullptr);
 }
-template <int ALGO, int BLOCK, bool HAS_PEERS, typename OffT, typename ValT>
+template <int ALGO, int BLOCK, int HAS_PEERS, typename OffT, typename ValT>
 __global__ void __launch_bounds__(BLOCK) merge_tile_reg_kernel(MERGE_REG_KERNEL_ARGS) {
     merge_tile_dispatch<ALGO, BLOCK, HAS_PEERS, false, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers,
                                                                    coords_x, carry_row, carry_val, nullptr);
 }
 // the hot-x variant: Aj is the plan's remapped copy
-template <int ALGO, int BLOCK, bool HAS_PEERS, typename OffT, typename ValT>
+template <int ALGO, int BLOCK, int HAS_PEERS, typename OffT, typename ValT>
 __global__ void __launch_bounds__(BLOCK, 2048 / BLOCK)
 merge_tile_hot_kernel_occ8(MERGE_REG_KERNEL_ARGS, const ValT *__restrict__ x_hot_biased) {
     merge_tile_dispatch<ALGO, BLOCK, HAS_PEERS, true, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers,
                                                                   coords_x, carry_row, carry_val, x_hot_biased);
 }
-template <int ALGO, int BLOCK, bool HAS_PEERS, typename OffT, typename ValT>
+template <int ALGO, int BLOCK, int HAS_PEERS, typename OffT, typename ValT>
 __global__ void __launch_bounds__(BLOCK)
 merge_tile_hot_kernel(MERGE_REG_KERNEL_ARGS, const ValT *__restrict__ x_hot_biased) {
     merge_tile_dispatch<ALGO, BLOCK, HAS_PEERS, true, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers,
@@ -1066,6 +1090,8 @@ int launch_merge(const SpmvProblem<OffT, ValT> &p) {
         // it without spilling (fp32: both forms with 32-bit offsets, the marker form with 64-bit;
         // fp64 needs 48-64 registers either way)
         const bool occ = sizeof(ValT) == 4 && (sizeof(OffT) == 4 || !flags_form);
+        // multicast peers (one pointer): its own fp32 flag-form variant, 8 CTAs per SM
+        const bool mc_f32 = p.peers.n < 0 && sizeof(ValT) == 4 && flags_form;
         // hot-x plan (hotx.cu): by default only for a caller that vouches for an unchanged matrix
         // and an x far longer than the TLB and the L2 reach
         const int64_t hot_opt = option_get("hot_x", -1);
@@ -1081,25 +1107,32 @@ int launch_merge(const SpmvProblem<OffT, ValT> &p) {
         if (hot) {
             const ValT *x_hot = nullptr;
             SPMV_TRY(hot_gather<ValT>(*hot, p.x, p.stream, &x_hot));
-            auto kernel = flags_form ? (has_peers ? merge_tile_hot_kernel<1, RB, true, OffT, ValT>
-                                                  : merge_tile_hot_kernel<1, RB, false, OffT, ValT>)
-                                     : (has_peers ? merge_tile_hot_kernel<0, RB, true, OffT, ValT>
-                                        : occ     ? merge_tile_hot_kernel_occ8<0, RB, false, OffT, ValT>
-                                                  : merge_tile_hot_kernel<0, RB, false, OffT, ValT>);
+            auto kernel = flags_form ? (mc_f32    ? merge_tile_hot_kernel<1, RB, 2, OffT, ValT>
+                                        : has_peers ? merge_tile_hot_kernel<1, RB, 1, OffT, ValT>
+                                                  : merge_tile_hot_kernel<1, RB, 0, OffT, ValT>)
+                                     : (has_peers ? merge_tile_hot_kernel<0, RB, 1, OffT, ValT>
+                                        : occ     ? merge_tile_hot_kernel_occ8<0, RB, 0, OffT, ValT>
+                                                  : merge_tile_hot_kernel<0, RB, 0, OffT, ValT>);
             SPMV_TRY(apply_carveout(reinterpret_cast<const void *>(kernel), carveout));
             const ValT *x_hot_biased = x_hot - ((ptrdiff_t)1 << 31);
+            if (option_get("hot_x_pdl", 1) > 0) {
+                cudaLaunchAttribute &a = lc.attrs[lc.cfg.numAttrs++];
+                a.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                a.val.programmaticStreamSerializationAllowed = 1;
+            }
             KernelTimerScope timed(p.stream);
             SPMV_CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, kernel, p.n_rows, p.nnz, p.Ap, hot->Aj2, p.Ax, p.x, p.y,
                                              p.alpha_dev, p.peers, (const int32_t *)coords,
                                              static_cast<int32_t *>(crow), static_cast<ValT *>(cval),
                                              x_hot_biased));
         } else {
-            auto kernel = flags_form ? (has_peers ? merge_tile_reg_kernel<1, RB, true, OffT, ValT>   // 40 regs, no spill
-                                        : occ     ? merge_tile_reg_kernel_occ8<1, RB, false, OffT, ValT>
-                                                  : merge_tile_reg_kernel<1, RB, false, OffT, ValT>)
-                                     : (has_peers ? merge_tile_reg_kernel<0, RB, true, OffT, ValT>
-                                        : occ     ? merge_tile_reg_kernel_occ8<0, RB, false, OffT, ValT>
-                                                  : merge_tile_reg_kernel<0, RB, false, OffT, ValT>);
+            auto kernel = flags_form ? (mc_f32    ? merge_tile_reg_kernel<1, RB, 2, OffT, ValT>
+                                        : has_peers ? merge_tile_reg_kernel<1, RB, 1, OffT, ValT>   // 40 regs, no spill
+                                        : occ     ? merge_tile_reg_kernel_occ8<1, RB, 0, OffT, ValT>
+                                                  : merge_tile_reg_kernel<1, RB, 0, OffT, ValT>)
+                                     : (has_peers ? merge_tile_reg_kernel<0, RB, 1, OffT, ValT>
+                                        : occ     ? merge_tile_reg_kernel_occ8<0, RB, 0, OffT, ValT>
+                                                  : merge_tile_reg_kernel<0, RB, 0, OffT, ValT>);
             SPMV_TRY(apply_carveout(reinterpret_cast<const void *>(kernel), carveout));
             KernelTimerScope timed(p.stream);
             SPMV_CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, kernel, p.n_rows, p.nnz, p.Ap, p.Aj, p.Ax, p.x, p.y,

@@ -32,6 +32,7 @@ struct spmvb200_power {
         void *alpha = nullptr;
         int *error = nullptr;
         cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        int64_t calls = 0;  // SpMVs issued on this GPU's row block since it was uploaded
     };
     std::vector<Gpu> gpu;
     std::vector<int64_t> row_bounds;
@@ -321,7 +322,9 @@ int spmvb200_power_steps(spmvb200_power_t *p, int steps) {
             a.y_peers = peers;
             a.n_peers = np;
             a.stream = G.stream;
-            a.flags = p->step > 0 ? SPMVB200_FLAG_STATIC_PATTERN : 0;
+            // the row block is resident and never changes: every call after the first vouches for
+            // it (a reset restarts the iteration, not the matrix)
+            a.flags = G.calls++ > 0 ? SPMVB200_FLAG_STATIC_PATTERN : 0;
             if (G.rows > 0) SPMV_TRY(spmvb200_spmv(&a));
             // Rows without nonzeros are never sent to the peers, so their entries must already be 0
             // in every replica: buffer 1 starts zeroed; buffer 0 held x0 and is cleared after the

@@ -57,6 +57,8 @@ std::map<std::string, int64_t> &options() {
                                  // passes SPMVB200_FLAG_STATIC_PATTERN and x is longer than
                                  // "hot_x_min_bytes"; 0 = never; 1 = always (plan keyed on the Aj pointer)
         {"hot_x_min_bytes", 256ll << 20},
+        {"hot_x_pdl", 1},        // 1: the hot-x tile kernel is launched with programmatic stream serialization
+        {"hot_x_fill", 0},       // how x_hot is refilled: 0/1 = gather x[hot_cols[r]], 2 = sweep over x, 3 = not at all (experiments)
         {"hot_x_max_bytes", 32ll << 20},   // size of the dense copy of the hot columns' x
         {"stream_ctas_per_sm", 3},  // persistent CTAs per SM of the CSR-stream kernel
         {"cusparse_alg", 0},     // 0: CUSPARSE_SPMV_ALG_DEFAULT (the reference's call), 1: CSR_ALG1, 2: CSR_ALG2

@@ -67,19 +67,27 @@ void choose(spmvb200_row_stats_t &st) {
         st.chosen_kind = (int32_t)forced;
         return;
     }
-    // Regular matrices (every row within a few vector steps of the mean) take the
-    // CSR-vector kernel; anything with a heavy tail takes merge-path, whose cost does not
-    // depend on how the nonzeros are spread over rows.
+    // Regular matrices (every row close to the mean) take the CSR-vector kernel, whose sub-warp
+    // width is picked from the mean; anything else takes merge-path, whose cost does not depend
+    // on how the nonzeros are spread over rows.  Thresholds from tools/selector_sweep.py
+    // (profiles/r2_selector_sweep.txt, 13 matrices between regular and power-law, 4 Mi rows): a
+    // sub-warp sized for the mean already loses to merge-path at std = 0.5 mean (rows of 1..31
+    // nonzeros: 358 us against 310; log-normal sigma 0.5: 368 against 310; half the rows empty:
+    // 344 against 312), so the line is drawn at 0.4 mean.  The dynamic-row kernel ("light") is
+    // never the fastest of the four on any of the 13 and is not selected.
     const double mean = st.mean_row_len > 1.0 ? st.mean_row_len : 1.0;
     const bool heavy_tail = (double)st.max_row_len > 16.0 * mean + 64.0 ||
-                            st.std_row_len > 1.5 * mean;
+                            st.std_row_len > 0.4 * mean;
     const bool mostly_empty = st.n_rows > 0 && st.empty_rows * 2 > st.n_rows;
     st.chosen_kind = (heavy_tail || mostly_empty) ? SPMVB200_KIND_MERGE : SPMVB200_KIND_VECTOR;
     // Short regular rows: a sub-warp per row wastes most of its 128-bit load slots (a 5-nonzero
     // row fills 5 of 8) and every row is a chain of dependent round trips; the CSR-stream kernel
     // moves the matrix with TMA bulk copies and gives a row to a thread.  Only worth its pipeline
     // on a matrix large enough to fill the persistent grid a few times over.
-    if (st.chosen_kind == SPMVB200_KIND_VECTOR && st.mean_row_len <= 8.0 && st.max_row_len <= 64 &&
+    // Up to 6 nonzeros per row: at 8 the thread-per-row reads of the staged tile are 8-way bank
+    // conflicts and the 2-lane CSR-vector kernel wins (band matrix, 8 per row: 86 us against 70);
+    // at 3 and 5 per row it is 70 against 82 and 20.5 against 22.5 us.
+    if (st.chosen_kind == SPMVB200_KIND_VECTOR && st.mean_row_len <= 6.0 && st.max_row_len <= 64 &&
         st.n_rows >= (int64_t)1 << 16)
         st.chosen_kind = SPMVB200_KIND_STREAM;
 }

@@ -2,7 +2,7 @@
 // memory by TMA bulk copies, one thread per row.
 //
 // The kernel for matrices of short, regular rows (the 5-point Laplacian of BASELINE.json's first
-// configuration; the selector routes mean <= 8 and max <= 64 nonzeros per row here).  It covers
+// configuration; the selector routes mean <= 6 and max <= 64 nonzeros per row here).  It covers
 // the case the reference gives to its CSR-vector kernels with 2- and 4-lane vectors
 // (reference/include/spmv/cusp/cusp.cuh:23-142 with THREADS_PER_VECTOR = 2/4, :189-203): there a
 // 5-nonzero row occupies 2 lanes x 4 load slots (3 of 8 wasted), every lane starts from an

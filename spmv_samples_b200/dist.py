@@ -159,6 +159,7 @@ class PowerIteration:
         self._tail_off = (self.n * item + 255) // 256 * 256
         self._alloc_elems = (self._tail_off + MAILBOX_BYTES + item - 1) // item
         self._xchg_step = 0         # never reset: the mailbox slots are addressed by it
+        self._calls_on_shard = 0    # SpMVs issued on the current shard (reset() keeps the matrix)
         if host_ops is None:
             if not torch.cuda.is_available():
                 raise RuntimeError("PowerIteration needs a CUDA device; there is no CPU path")
@@ -286,11 +287,12 @@ class PowerIteration:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 self._local_events.append(ev)
                 ev[0].record()
-            # the shard never changes between steps: from the second step on the merge-path
-            # partition of the previous call is reused
+            # the shard never changes between steps: from its second SpMV on, what earlier calls
+            # derived from it (tile coordinates, the hot-x plan) is reused
             spmv_mod.spmv_ex(self.kind, m.Ap, m.Aj, m.Ax, x, y, n_cols=self.n, alpha_dev=self.alpha,
                              y_peers=peers, multicast=self.exchange == "mc",
-                             static_pattern=self.step_no > 0)
+                             static_pattern=self._calls_on_shard > 0)
+            self._calls_on_shard += 1
             if self.step_no == 0 and self.exchange in ("p2p", "mc"):
                 # The kernels send only rows that have nonzeros to the peers; an empty row's
                 # entry must therefore already be 0 in every replica.  Buffer 1 starts zeroed;
@@ -343,6 +345,7 @@ class PowerIteration:
         if shard.world != self.world or shard.rank != self.rank or shard.csr.n_cols != self.n:
             raise ValueError("set_shard: the new shard must belong to the same matrix and rank")
         self.shard = shard
+        self._calls_on_shard = 0
         self.reset()
 
     def shard_local_ms(self, steps: int = 5):
