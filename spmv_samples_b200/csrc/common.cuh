@@ -77,6 +77,16 @@ void scratch_release_all();
 
 int64_t option_get(const char *name, int64_t fallback);
 
+// A small kernel that a big one depends on (the merge-path partition, the refill of x_hot) is
+// launched on a per-device side stream, forked from and joined to the caller's stream with events:
+//     cudaStream_t side;  side_fork(stream, &side);  small<<<..., side>>>(...);  side_join(stream);
+// Launched on the caller's stream right in front of the big kernel, such a kernel is followed by
+// ~170 us of idle GPU before the big kernel starts (measured: tools/step_kernels.py,
+// profiles/r2_step_kernels.txt -- R-MAT scale 24: partition 17 us, idle 171 us, tile kernel 1081 us);
+// through the side stream the big kernel starts 2 us after the small one ends.
+int side_fork(cudaStream_t stream, cudaStream_t *side);
+int side_join(cudaStream_t stream);
+
 // cudaEvent bracket around the dominant kernel of a call (no-op unless "time_main_kernel")
 class KernelTimerScope {
 public:

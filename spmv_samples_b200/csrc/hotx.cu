@@ -128,37 +128,6 @@ hot_bitmap_kernel(const uint32_t *__restrict__ counts, const uint32_t *__restric
     }
 }
 
-// x_hot by compaction: a warp reads 32 consecutive values of x (one line) wherever at least one of
-// them is hot and writes the hot ones to consecutive slots.  Against the gather below: the hot
-// columns of R-MAT scale 27 are 1 in 16, so a gather pulls a 128-byte line per 4 useful bytes
-// (1.07 GB, ~200 us per SpMV); the sweep reads at most x once (0.5 GB) and skips words without a
-// hot column.
-template <typename ValT>
-__global__ void __launch_bounds__(256)
-hot_compact_kernel(const ValT *__restrict__ x, const uint32_t *__restrict__ bitmap,
-                   const uint32_t *__restrict__ rank32, int64_t words, int64_t n_cols, ValT *__restrict__ x_hot) {
-    const int lane = threadIdx.x & 31;
-    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < words;
-         w += ((int64_t)gridDim.x * blockDim.x) >> 5) {
-        const unsigned mask = __ldg(bitmap + w);
-        if (mask == 0u) continue;
-        const int64_t c = w * 32 + lane;
-        if ((mask >> lane) & 1u)
-            x_hot[__ldg(rank32 + w) + __popc(mask & ((1u << lane) - 1u))] = __ldg(x + c);
-    }
-}
-
-template <typename ValT>
-__global__ void __launch_bounds__(256)
-hot_gather_kernel(const ValT *__restrict__ x, const int32_t *__restrict__ hot_cols, int64_t K,
-                  ValT *__restrict__ x_hot) {
-    // the tile kernel behind this one may start being set up now (it waits for this grid to
-    // complete before it reads anything: griddepcontrol.wait in merge.cu)
-    asm volatile("griddepcontrol.launch_dependents;");
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < K; r += (int64_t)gridDim.x * blockDim.x)
-        x_hot[r] = __ldg(x + __ldg(hot_cols + r));
-}
-
 struct PlanEntry {
     HotPlan plan;
     int64_t nnz = 0;
@@ -335,64 +304,5 @@ void hot_plan_drop(const int32_t *Aj) {
     g_plans.erase(it);
 }
 
-// experiments (option hot_x_fill 4..7): what about the refill kernel makes the GPU idle after it?
-template <typename ValT>
-__global__ void __launch_bounds__(256)
-hot_probe_kernel(int mode, const ValT *__restrict__ x, const int32_t *__restrict__ hot_cols, int64_t K,
-                 ValT *__restrict__ x_hot, ValT *__restrict__ sink) {
-    ValT acc = (ValT)0;
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < K; r += (int64_t)gridDim.x * blockDim.x) {
-        if (mode == 4) acc += __ldg(x + __ldg(hot_cols + r));          // reads only
-        else if (mode == 5) x_hot[r] = (ValT)r;                           // writes only
-        else if (mode == 6) x_hot[r] = __ldg(x + r);                      // dense read of x's head + write
-    }
-    if (acc == (ValT)123.456) sink[0] = acc;
-}
-
-template <typename ValT>
-int hot_gather(const HotPlan &plan, const ValT *x, cudaStream_t stream, const ValT **x_hot) {
-    const DeviceInfo *di = nullptr;
-    SPMV_TRY(current_device_info(&di));
-    void *buf = nullptr;
-    SPMV_TRY(scratch_get(stream, SCRATCH_XHOT, (size_t)plan.K * sizeof(ValT), &buf));
-    *x_hot = static_cast<const ValT *>(buf);
-    const int64_t cap = (int64_t)di->sm_count * 16;
-    // "hot_x_fill": 0 / 1 = gather x[hot_cols[r]] (the default: 32 us for 8.4 M columns of R-MAT
-    // scale 27), 2 = sweep over x with the bitmap (143 us there: it reads 16x more of x than it
-    // keeps), 3 = no refill at all (timing experiments only: x_hot goes stale)
-    const int64_t fill = option_get("hot_x_fill", 0);
-    if (fill == 3) return SPMVB200_OK;
-    if (fill >= 4 && fill <= 6) {
-        int64_t blocks = (plan.K + 255) / 256;
-        if (blocks > cap) blocks = cap;
-        hot_probe_kernel<ValT><<<(unsigned)blocks, 256, 0, stream>>>((int)fill, x, plan.hot_cols, plan.K,
-                                                                     static_cast<ValT *>(buf), static_cast<ValT *>(buf));
-        SPMV_LAUNCH_CHECK();
-        return SPMVB200_OK;
-    }
-    if (fill == 7) {   // the real refill on 148 CTAs
-        hot_gather_kernel<ValT><<<(unsigned)di->sm_count, 256, 0, stream>>>(x, plan.hot_cols, plan.K,
-                                                                            static_cast<ValT *>(buf));
-        SPMV_LAUNCH_CHECK();
-        return SPMVB200_OK;
-    }
-    const bool sweep = fill == 2;
-    if (sweep) {
-        const int64_t words = ((int64_t)plan.n_cols + 31) / 32;
-        int64_t blocks = (words * 32 + 255) / 256;
-        if (blocks > cap) blocks = cap;
-        hot_compact_kernel<ValT><<<(unsigned)blocks, 256, 0, stream>>>(x, plan.bitmap, plan.rank32, words,
-                                                                       plan.n_cols, static_cast<ValT *>(buf));
-    } else {
-        int64_t blocks = (plan.K + 255) / 256;
-        if (blocks > cap) blocks = cap;
-        hot_gather_kernel<ValT><<<(unsigned)blocks, 256, 0, stream>>>(x, plan.hot_cols, plan.K,
-                                                                      static_cast<ValT *>(buf));
-    }
-    SPMV_LAUNCH_CHECK();
-    return SPMVB200_OK;
-}
-template int hot_gather<float>(const HotPlan &, const float *, cudaStream_t, const float **);
-template int hot_gather<double>(const HotPlan &, const double *, cudaStream_t, const double **);
 
 }  // namespace spmvb200

@@ -334,10 +334,9 @@ merge_tile_reg_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
     __shared__ __align__(16) unsigned char s_flag[SLOTS];
     __shared__ WarpTotal<ValT> s_w[BLOCK / 32];
 
-    // The hot-x kernel is launched with programmatic stream serialization right behind the small
-    // kernel that refills x_hot: it may be set up -- and its CTAs may arrive here -- while that
-    // kernel still runs; nothing is read before it has completed.  (Launched the ordinary way the
-    // GPU sat idle ~160 us between the two on R-MAT scale 27, profiles/r2_step_kernels.txt.)
+    // Option "hot_x_pdl": the hot-x kernel may be launched with programmatic stream serialization
+    // behind the kernel that refills x_hot; nothing is read before that kernel has completed.
+    // (Tried against the idle gap after the refill -- no effect; a no-op without the attribute.)
     if (HOT) asm volatile("griddepcontrol.wait;" ::: "memory");
     const int tid = threadIdx.x;
     const int64_t tile = blockIdx.x;
@@ -514,10 +513,9 @@ merge_tile_mark_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
     __shared__ __align__(16) unsigned short s_mark[SLOTS];   // slot -> 1 + row starting there, 0 = none
     __shared__ WarpTotal<ValT> s_w[BLOCK / 32];
 
-    // The hot-x kernel is launched with programmatic stream serialization right behind the small
-    // kernel that refills x_hot: it may be set up -- and its CTAs may arrive here -- while that
-    // kernel still runs; nothing is read before it has completed.  (Launched the ordinary way the
-    // GPU sat idle ~160 us between the two on R-MAT scale 27, profiles/r2_step_kernels.txt.)
+    // Option "hot_x_pdl": the hot-x kernel may be launched with programmatic stream serialization
+    // behind the kernel that refills x_hot; nothing is read before that kernel has completed.
+    // (Tried against the idle gap after the refill -- no effect; a no-op without the attribute.)
     if (HOT) asm volatile("griddepcontrol.wait;" ::: "memory");
     const int tid = threadIdx.x;
     const int64_t tile = blockIdx.x;
@@ -1010,9 +1008,14 @@ int launch_partition(int32_t n_rows, OffT nnz, const OffT *Ap, int64_t tile_item
     const PartitionTag tag{coords_x, Ap, (int64_t)n_rows, (int64_t)nnz, tile_items, n_coords};
     if (reuse && partition_tag_matches(stream, tag)) return SPMVB200_OK;
     const int64_t blocks = (n_coords + 255) / 256;
-    merge_partition_kernel<OffT><<<(unsigned)blocks, 256, 0, stream>>>(n_rows, nnz, Ap, tile_items,
-                                                                       n_coords, coords_x);
+    // on the side stream: see side_fork in common.cuh (171 us of idle GPU between this kernel and
+    // the tile kernel otherwise, on every call that does not reuse its coordinates)
+    cudaStream_t side = nullptr;
+    SPMV_TRY(side_fork(stream, &side));
+    merge_partition_kernel<OffT><<<(unsigned)blocks, 256, 0, side>>>(n_rows, nnz, Ap, tile_items,
+                                                                     n_coords, coords_x);
     SPMV_LAUNCH_CHECK();
+    SPMV_TRY(side_join(stream));
     partition_tag_store(stream, tag);
     return SPMVB200_OK;
 }
@@ -1115,7 +1118,7 @@ int launch_merge(const SpmvProblem<OffT, ValT> &p) {
                                                   : merge_tile_hot_kernel<0, RB, 0, OffT, ValT>);
             SPMV_TRY(apply_carveout(reinterpret_cast<const void *>(kernel), carveout));
             const ValT *x_hot_biased = x_hot - ((ptrdiff_t)1 << 31);
-            if (option_get("hot_x_pdl", 1) > 0) {
+            if (option_get("hot_x_pdl", 0) > 0) {
                 cudaLaunchAttribute &a = lc.attrs[lc.cfg.numAttrs++];
                 a.id = cudaLaunchAttributeProgrammaticStreamSerialization;
                 a.val.programmaticStreamSerializationAllowed = 1;

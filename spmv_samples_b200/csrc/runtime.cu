@@ -57,8 +57,11 @@ std::map<std::string, int64_t> &options() {
                                  // passes SPMVB200_FLAG_STATIC_PATTERN and x is longer than
                                  // "hot_x_min_bytes"; 0 = never; 1 = always (plan keyed on the Aj pointer)
         {"hot_x_min_bytes", 256ll << 20},
-        {"hot_x_pdl", 1},        // 1: the hot-x tile kernel is launched with programmatic stream serialization
-        {"hot_x_fill", 0},       // how x_hot is refilled: 0/1 = gather x[hot_cols[r]], 2 = sweep over x, 3 = not at all (experiments)
+        {"side_stream", 1},      // 1: small kernels a big one depends on (partition, x_hot refill) run on a side
+                                 // stream forked / joined with events; 0: on the caller's stream
+        {"hot_x_pdl", 0},        // 1: the hot-x tile kernel is launched with programmatic stream serialization (measured: no effect)
+        {"hot_x_fill", 0},       // how x_hot is refilled: 0 = gather on a side stream, 1 = gather on the caller's stream,
+                                 // 2 = sweep over x, 3 = not at all (experiments)
         {"hot_x_max_bytes", 32ll << 20},   // size of the dense copy of the hot columns' x
         {"stream_ctas_per_sm", 3},  // persistent CTAs per SM of the CSR-stream kernel
         {"cusparse_alg", 0},     // 0: CUSPARSE_SPMV_ALG_DEFAULT (the reference's call), 1: CSR_ALG1, 2: CSR_ALG2
@@ -151,6 +154,50 @@ void scratch_release_all() {
     }
     g_scratch.clear();
     if (cur >= 0) cudaSetDevice(cur);
+}
+
+namespace {
+struct SideLane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+std::map<int, SideLane> g_lanes;
+
+int side_lane(SideLane *out) {
+    int dev = -1;
+    SPMV_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_mu);
+    SideLane &l = g_lanes[dev];
+    if (!l.stream) {
+        SPMV_CUDA_TRY(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+        SPMV_CUDA_TRY(cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming));
+        SPMV_CUDA_TRY(cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming));
+    }
+    *out = l;
+    return SPMVB200_OK;
+}
+}  // namespace
+
+int side_fork(cudaStream_t stream, cudaStream_t *side) {
+    if (option_get("side_stream", 1) <= 0) {   // 0: everything on the caller's stream (A/B runs)
+        *side = stream;
+        return SPMVB200_OK;
+    }
+    SideLane lane;
+    SPMV_TRY(side_lane(&lane));
+    SPMV_CUDA_TRY(cudaEventRecord(lane.fork, stream));
+    SPMV_CUDA_TRY(cudaStreamWaitEvent(lane.stream, lane.fork, 0));
+    *side = lane.stream;
+    return SPMVB200_OK;
+}
+
+int side_join(cudaStream_t stream) {
+    if (option_get("side_stream", 1) <= 0) return SPMVB200_OK;
+    SideLane lane;
+    SPMV_TRY(side_lane(&lane));
+    SPMV_CUDA_TRY(cudaEventRecord(lane.join, lane.stream));
+    SPMV_CUDA_TRY(cudaStreamWaitEvent(stream, lane.join, 0));
+    return SPMVB200_OK;
 }
 
 int64_t option_get(const char *name, int64_t fallback) {

@@ -58,3 +58,27 @@ def test_driver_usage_and_missing_file():
     assert r.returncode == 1 and "usage:" in r.stderr
     r = run("/nonexistent/file.mtx", "merge")
     assert r.returncode == 1 and "File could not be opened" in r.stderr  # load.hpp:278-281
+
+
+def test_driver_accepts_the_reference_command_line():
+    """Every label of the reference's SPMV_KINDS (reference/include/spmv.h:18-27) on one command
+    line, as a user of the reference would type it, plus the new "stream" kind."""
+    kinds = ["cusparse", "cusp", "cusp1", "cusp2", "light_vec", "light_warp", "cub_merge", "merge",
+             "merge_genl", "stream"]
+    r = run("synthetic:c1:64", *kinds, "--iters", "3", "--x", "random")
+    assert r.returncode == 0, r.stdout + r.stderr
+    for k in kinds:
+        assert re.search(rf"\[{k}\s*\].*PASS", r.stdout), r.stdout
+
+
+def test_driver_power_iteration_from_one_process():
+    """main.cu --power K [--gpus N]: the row-sharded power iteration behind the C ABI
+    (csrc/multi.cu), no Python in the loop; on every GPU the box has, up to 8."""
+    n = min(torch.cuda.device_count(), 8)
+    for gpus in sorted({1, n}):
+        r = run("synthetic:c3:14", "merge", "--iters", "2", "--power", "12", "--gpus", str(gpus))
+        assert r.returncode == 0, r.stdout + r.stderr
+        m = re.search(r"\[power\s*\]\s+([0-9.]+) ms/step.*\|\|A x\|\| = ([0-9.e+-]+)", r.stdout)
+        assert m and float(m.group(1)) > 0 and float(m.group(2)) > 0, r.stdout
+        rows = re.search(r"rows per GPU:((?: \d+)+)", r.stdout)
+        assert rows and sum(int(v) for v in rows.group(1).split()) == 1 << 14

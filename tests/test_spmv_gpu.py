@@ -647,7 +647,7 @@ def test_reference_labels_are_aliases():
 
 
 # ------------------------------------------------------------------ hot-x plan (csrc/hotx.cu)
-@pytest.mark.parametrize("fill", [1, 2])
+@pytest.mark.parametrize("fill", [0, 1, 2])
 @pytest.mark.parametrize("off", [np.int32, np.int64])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_hot_x_plan_is_bit_identical(dtype, off, fill):
