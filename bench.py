@@ -65,6 +65,7 @@ def parse_args():
     p.add_argument("--cpu-seconds", type=float, default=15.0,
                    help="budget of the cpu_baseline leg (own arm)")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--opts", default="", help="library options name=value,... (experiments; recorded in config)")
     p.add_argument("--no-configs", action="store_true",
                    help="skip the c1..c4 + cuSPARSE leg (N = 1 only; outside the timed region)")
     return p.parse_args()
@@ -535,6 +536,9 @@ def own_arm(args, rank, world, local_rank):
     # diagnostics only (the contract line needs both): BENCH_NO_KTIMER=1 leaves the per-kernel
     # event timer off, BENCH_NO_SAMPLER=1 the NVML clock sampler
     spmv.set_option("time_main_kernel", 0 if os.environ.get("BENCH_NO_KTIMER") else 1)
+    for kv in filter(None, args.opts.split(",")):
+        name, v = kv.split("=")
+        spmv.set_option(name, int(v))
     peak, peak_src = measured_peak()
 
     # ---- the matrix: every rank builds the global CSR on its own GPU, keeps its rows
@@ -757,6 +761,7 @@ def own_arm(args, rank, world, local_rank):
                 "step": "one power-iteration SpMV (x <- A x / ||A x||) over the whole matrix, "
                         "incl. x exchange and norm",
                 "kind": args.kind, "selected_kernel": kind_names.get(stats["chosen_kind"]),
+                "library_options": args.opts or None,
                 "exchange": exchange_used, "exchange_note": exchange_note, "parallelism": f"row-sharded x{world} (merge-path nnz split, row weight {args.row_weight}"
                                 + (f", re-split {args.rebalance}x from measured per-rank local step times)" if world > 1 and args.rebalance else ")"),
                 "rebalance": rebalance_log,

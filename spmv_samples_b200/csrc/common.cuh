@@ -77,13 +77,15 @@ void scratch_release_all();
 
 int64_t option_get(const char *name, int64_t fallback);
 
-// A small kernel that a big one depends on (the merge-path partition, the refill of x_hot) is
-// launched on a per-device side stream, forked from and joined to the caller's stream with events:
-//     cudaStream_t side;  side_fork(stream, &side);  small<<<..., side>>>(...);  side_join(stream);
-// Launched on the caller's stream right in front of the big kernel, such a kernel is followed by
-// ~170 us of idle GPU before the big kernel starts (measured: tools/step_kernels.py,
-// profiles/r2_step_kernels.txt -- R-MAT scale 24: partition 17 us, idle 171 us, tile kernel 1081 us);
-// through the side stream the big kernel starts 2 us after the small one ends.
+// Option "side_stream" (default 0): a small kernel that a big one depends on (the merge-path
+// partition, the refill of x_hot) is launched on a side stream, forked from and joined to the
+// caller's stream with events.  Built against a ~170 us idle gap that the CUPTI timeline
+// (tools/step_kernels.py, torch profiler) shows between such a kernel and the tile kernel behind
+// it -- and which the fork / join removes *in that timeline*.  Event timing outside the profiler
+// shows no such gap (back-to-back R-MAT scale 24 SpMVs: 1121 us without, 1124 us with the side
+// stream; power-iteration step 11.13 / 11.16 ms), and the extra streams cost the three-slot
+// host-buffer pipeline its overlap (11.7 -> 19.0 ms per step end to end).  A profiler artefact:
+// off.  profiles/r2_step_kernels.txt keeps the whole chase.
 int side_fork(cudaStream_t stream, cudaStream_t *side);
 int side_join(cudaStream_t stream);
 
@@ -173,7 +175,7 @@ int gather_yardstick(int64_t n_x, int64_t count, int reps, cudaStream_t stream, 
 // Launch attribute helper: optional L2 access-policy window over x (option "l2_window").
 struct LaunchCfg {
     cudaLaunchConfig_t cfg;
-    cudaLaunchAttribute attrs[3];
+    cudaLaunchAttribute attrs[2];
 };
 void make_launch_cfg(LaunchCfg &lc, dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                      const void *x, size_t x_bytes);

@@ -1,13 +1,7 @@
 // hotx_fill.cu -- the per-call half of the hot-x plan (hotx.cu builds it): x_hot[r] = x[hot_cols[r]].
 //
-// The refill kernel runs on a side stream, forked from and joined to the caller's stream with
-// events.  Launched on the caller's stream right in front of the tile kernel it is followed by
-// ~165 us during which the GPU is idle (R-MAT scale 27; tools/step_kernels.py, profiles/
-// r2_step_kernels.txt): the gap follows the refill whatever it does (reads only, writes only, a
-// no-op <<<1,1>>>), whatever translation unit it is compiled in and however it is launched, moves
-// in front of a spacer kernel put behind it, and is not removed by programmatic dependent launch;
-// a kernel launched from a separate host call in front of the SpMV shows it or not depending on
-// the kernel.  With the fork / join it is gone and the step is 230 us shorter (11.16 -> 10.93 ms).
+// 32 us per SpMV on R-MAT scale 27 (8.4 M hot columns).  Kept apart from hotx.cu, which pulls in CUB
+// for the plan build.
 #include "common.cuh"
 
 namespace spmvb200 {
@@ -51,9 +45,9 @@ int hot_gather(const HotPlan &plan, const ValT *x, cudaStream_t stream, const Va
     SPMV_TRY(scratch_get(stream, SCRATCH_XHOT, (size_t)plan.K * sizeof(ValT), &buf));
     *x_hot = static_cast<const ValT *>(buf);
     const int64_t cap = (int64_t)di->sm_count * 16;
-    // "hot_x_fill": 0 = gather x[hot_cols[r]] on the side stream (default), 1 = the same on the
-    // caller's stream, 2 = sweep over x with the bitmap on the caller's stream, 3 = no refill at
-    // all (timing experiments only: x_hot goes stale)
+    // "hot_x_fill": 0 / 1 = gather x[hot_cols[r]] (0 goes through side_fork / side_join, which is
+    // the caller's stream unless option "side_stream" is on), 2 = sweep over x with the bitmap,
+    // 3 = no refill at all (timing experiments only: x_hot goes stale)
     const int64_t fill = option_get("hot_x_fill", 0);
     if (fill == 3) return SPMVB200_OK;
     if (fill == 2) {

@@ -10,7 +10,7 @@
 // agent's per-thread path search + serial merge (about 45 scalar shared-memory operations per
 // thread) is shared-memory-issue bound here (first ncu capture: mio_throttle + short
 // scoreboard dominant, 75 thread instructions per path item, 16 % of the HBM roofline):
-//   * a tile is 1020 path items (128 threads, int32 offsets) or 2044 (256 threads, int64);
+//   * a tile is 1020 path items (128 threads; the TMA-staged ablation kernel keeps 256 / 2044);
 //   * every thread owns 8 consecutive nonzeros: 128-bit evict-first loads of Aj and Ax from a
 //     16-byte aligned position straight into registers, x gathered with an L2 evict-last
 //     policy, products kept in registers (merge_tile_reg_body, the default).  The first version
@@ -334,10 +334,6 @@ merge_tile_reg_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
     __shared__ __align__(16) unsigned char s_flag[SLOTS];
     __shared__ WarpTotal<ValT> s_w[BLOCK / 32];
 
-    // Option "hot_x_pdl": the hot-x kernel may be launched with programmatic stream serialization
-    // behind the kernel that refills x_hot; nothing is read before that kernel has completed.
-    // (Tried against the idle gap after the refill -- no effect; a no-op without the attribute.)
-    if (HOT) asm volatile("griddepcontrol.wait;" ::: "memory");
     const int tid = threadIdx.x;
     const int64_t tile = blockIdx.x;
     const int64_t total = (int64_t)n_rows + (int64_t)nnz;
@@ -513,10 +509,6 @@ merge_tile_mark_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
     __shared__ __align__(16) unsigned short s_mark[SLOTS];   // slot -> 1 + row starting there, 0 = none
     __shared__ WarpTotal<ValT> s_w[BLOCK / 32];
 
-    // Option "hot_x_pdl": the hot-x kernel may be launched with programmatic stream serialization
-    // behind the kernel that refills x_hot; nothing is read before that kernel has completed.
-    // (Tried against the idle gap after the refill -- no effect; a no-op without the attribute.)
-    if (HOT) asm volatile("griddepcontrol.wait;" ::: "memory");
     const int tid = threadIdx.x;
     const int64_t tile = blockIdx.x;
     const int64_t total = (int64_t)n_rows + (int64_t)nnz;
@@ -1008,8 +1000,7 @@ int launch_partition(int32_t n_rows, OffT nnz, const OffT *Ap, int64_t tile_item
     const PartitionTag tag{coords_x, Ap, (int64_t)n_rows, (int64_t)nnz, tile_items, n_coords};
     if (reuse && partition_tag_matches(stream, tag)) return SPMVB200_OK;
     const int64_t blocks = (n_coords + 255) / 256;
-    // on the side stream: see side_fork in common.cuh (171 us of idle GPU between this kernel and
-    // the tile kernel otherwise, on every call that does not reuse its coordinates)
+    // optionally on a side stream (option "side_stream", off: see side_fork in common.cuh)
     cudaStream_t side = nullptr;
     SPMV_TRY(side_fork(stream, &side));
     merge_partition_kernel<OffT><<<(unsigned)blocks, 256, 0, side>>>(n_rows, nnz, Ap, tile_items,
@@ -1024,10 +1015,16 @@ template int launch_partition<int32_t>(int32_t, int32_t, const int32_t *, int64_
 template int launch_partition<int64_t>(int32_t, int64_t, const int64_t *, int64_t, int64_t,
                                        int32_t *, cudaStream_t, bool);
 
-// CTA size of the register-staged tile kernel: 128 threads (1020-item tiles) with 32-bit offsets,
-// 256 threads (2044-item tiles) with 64-bit offsets -- measured: 128 is 3-8 % faster on c2/c3/c4
-// (shorter barrier waits, 16 CTAs per SM) and 2 % slower on c5.
-template <typename OffT> constexpr int merge_reg_block() { return sizeof(OffT) == 4 ? 128 : 256; }
+// CTA size of the register-staged tile kernel: 128 threads (1020-item tiles) -- measured: 128 is
+// 3-8 % faster than 256 on c2/c3/c4 (shorter barrier waits, 16 CTAs per SM) and, since the hot-x
+// plan, 4 % faster on c5 as well.
+// 64-bit offsets used 256-thread CTAs (2044-item tiles) while R-MAT scale 27 was bound by the TLB
+// and the DRAM (2 % ahead of 128 there); with the hot-x plan the kernel is L1TEX-bound like the
+// 32-bit one and 128 threads win: tile kernel 10.74 -> 10.31 ms, step 10.92 -> 10.52 ms.
+#ifndef SPMV_MERGE_O64_BLOCK
+#define SPMV_MERGE_O64_BLOCK 128
+#endif
+template <typename OffT> constexpr int merge_reg_block() { return sizeof(OffT) == 4 ? 128 : SPMV_MERGE_O64_BLOCK; }
 
 int64_t merge_tile_items(int offset_bits) {
     if (option_get("merge_staging", 0) == 1) return kMergeTile;
@@ -1089,7 +1086,7 @@ int launch_merge(const SpmvProblem<OffT, ValT> &p) {
         // 65536 x 2048 matrix (no second pass over Ap, one barrier less).
         const int64_t algo_opt = option_get("merge_algo", -1);
         const bool flags_form = algo_opt < 0 ? sizeof(ValT) == 4 : algo_opt == 1;
-        // 8 CTAs of 256 threads per SM need 32 registers: the bound is only applied where ptxas meets
+        // 16 CTAs of 128 threads per SM need 32 registers: the bound is only applied where ptxas meets
         // it without spilling (fp32: both forms with 32-bit offsets, the marker form with 64-bit;
         // fp64 needs 48-64 registers either way)
         const bool occ = sizeof(ValT) == 4 && (sizeof(OffT) == 4 || !flags_form);
@@ -1118,11 +1115,6 @@ int launch_merge(const SpmvProblem<OffT, ValT> &p) {
                                                   : merge_tile_hot_kernel<0, RB, 0, OffT, ValT>);
             SPMV_TRY(apply_carveout(reinterpret_cast<const void *>(kernel), carveout));
             const ValT *x_hot_biased = x_hot - ((ptrdiff_t)1 << 31);
-            if (option_get("hot_x_pdl", 0) > 0) {
-                cudaLaunchAttribute &a = lc.attrs[lc.cfg.numAttrs++];
-                a.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-                a.val.programmaticStreamSerializationAllowed = 1;
-            }
             KernelTimerScope timed(p.stream);
             SPMV_CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, kernel, p.n_rows, p.nnz, p.Ap, hot->Aj2, p.Ax, p.x, p.y,
                                              p.alpha_dev, p.peers, (const int32_t *)coords,

@@ -6,6 +6,7 @@
 // merge_based/merge_based.cuh:34,46 -- the last one leaks) with buffers that are allocated
 // once and grown on demand, so the steady-state call makes no allocation and no sync.
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -57,15 +58,34 @@ std::map<std::string, int64_t> &options() {
                                  // passes SPMVB200_FLAG_STATIC_PATTERN and x is longer than
                                  // "hot_x_min_bytes"; 0 = never; 1 = always (plan keyed on the Aj pointer)
         {"hot_x_min_bytes", 256ll << 20},
-        {"side_stream", 1},      // 1: small kernels a big one depends on (partition, x_hot refill) run on a side
-                                 // stream forked / joined with events; 0: on the caller's stream
-        {"hot_x_pdl", 0},        // 1: the hot-x tile kernel is launched with programmatic stream serialization (measured: no effect)
-        {"hot_x_fill", 0},       // how x_hot is refilled: 0 = gather on a side stream, 1 = gather on the caller's stream,
-                                 // 2 = sweep over x, 3 = not at all (experiments)
+        {"side_stream", 0},      // 1: small kernels a big one depends on (partition, x_hot refill) run on a side
+                                 // stream forked / joined with events (measured: no gain outside the profiler)
+        {"hot_x_fill", 0},       // how x_hot is refilled: 0/1 = gather x[hot_cols[r]], 2 = sweep over x, 3 = not at all (experiments)
         {"hot_x_max_bytes", 32ll << 20},   // size of the dense copy of the hot columns' x
         {"stream_ctas_per_sm", 3},  // persistent CTAs per SM of the CSR-stream kernel
         {"cusparse_alg", 0},     // 0: CUSPARSE_SPMV_ALG_DEFAULT (the reference's call), 1: CSR_ALG1, 2: CSR_ALG2
     };
+    // SPMVB200_OPTS="name=value,name=value": presets for callers without an option API of their
+    // own (the C++ driver), read once
+    static bool env_read = false;
+    if (!env_read) {
+        env_read = true;
+        if (const char *e = std::getenv("SPMVB200_OPTS")) {
+            std::string s(e);
+            size_t pos = 0;
+            while (pos < s.size()) {
+                size_t end = s.find(',', pos);
+                if (end == std::string::npos) end = s.size();
+                const std::string kv = s.substr(pos, end - pos);
+                const size_t eq = kv.find('=');
+                if (eq != std::string::npos) {
+                    auto it = o.find(kv.substr(0, eq));
+                    if (it != o.end()) it->second = std::atoll(kv.c_str() + eq + 1);
+                }
+                pos = end + 1;
+            }
+        }
+    }
     return o;
 }
 }  // namespace
@@ -161,13 +181,14 @@ struct SideLane {
     cudaStream_t stream = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
 };
-std::map<int, SideLane> g_lanes;
+// one side stream per (device, caller stream)
+std::map<std::pair<int, cudaStream_t>, SideLane> g_lanes;
 
-int side_lane(SideLane *out) {
+int side_lane(cudaStream_t stream, SideLane *out) {
     int dev = -1;
     SPMV_CUDA_TRY(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lk(g_mu);
-    SideLane &l = g_lanes[dev];
+    SideLane &l = g_lanes[{dev, stream}];
     if (!l.stream) {
         SPMV_CUDA_TRY(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
         SPMV_CUDA_TRY(cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming));
@@ -179,12 +200,12 @@ int side_lane(SideLane *out) {
 }  // namespace
 
 int side_fork(cudaStream_t stream, cudaStream_t *side) {
-    if (option_get("side_stream", 1) <= 0) {   // 0: everything on the caller's stream (A/B runs)
+    if (option_get("side_stream", 0) <= 0) {   // the default: everything on the caller's stream
         *side = stream;
         return SPMVB200_OK;
     }
     SideLane lane;
-    SPMV_TRY(side_lane(&lane));
+    SPMV_TRY(side_lane(stream, &lane));
     SPMV_CUDA_TRY(cudaEventRecord(lane.fork, stream));
     SPMV_CUDA_TRY(cudaStreamWaitEvent(lane.stream, lane.fork, 0));
     *side = lane.stream;
@@ -192,9 +213,9 @@ int side_fork(cudaStream_t stream, cudaStream_t *side) {
 }
 
 int side_join(cudaStream_t stream) {
-    if (option_get("side_stream", 1) <= 0) return SPMVB200_OK;
+    if (option_get("side_stream", 0) <= 0) return SPMVB200_OK;
     SideLane lane;
-    SPMV_TRY(side_lane(&lane));
+    SPMV_TRY(side_lane(stream, &lane));
     SPMV_CUDA_TRY(cudaEventRecord(lane.join, lane.stream));
     SPMV_CUDA_TRY(cudaStreamWaitEvent(stream, lane.join, 0));
     return SPMVB200_OK;
