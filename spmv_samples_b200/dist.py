@@ -130,14 +130,14 @@ class PowerIteration:
     """x <- A x / ||A x||, A row-sharded over `world` ranks (world = 1: the whole matrix)."""
 
     def __init__(self, shard: Shard, n_rows_global: int, kind: str = "auto", exchange: str = "auto",
-                 group=None, host_ops=None):
-        """host_ops: TEST HOOK ONLY -- an object with spmv(csr, x, y, alpha) for CPU tensors, so
-        the exchange protocol (double buffering, uneven all-gather, norm all-reduce) can be
-        exercised with the gloo backend where there is no GPU.  The product never passes it;
-        without it every step goes through libspmvb200 and needs CUDA."""
+                 group=None):
+        """Every step goes through libspmvb200 and needs CUDA.  The four device operations of a
+        step are methods (_setup_buffers, _local_spmv, _local_sumsq, _alpha_from_sumsq) so that
+        tests/test_dist_cpu.py can drive the exchange protocol -- double buffering, uneven
+        all-gather, norm all-reduce -- over gloo with a subclass of its own that replaces them by
+        the CPU oracle; this module contains no host arithmetic."""
         import torch.distributed as dist
         self.dist = dist
-        self.host_ops = host_ops
         self.shard = shard
         self.world, self.rank = shard.world, shard.rank
         self.kind = kind
@@ -160,49 +160,72 @@ class PowerIteration:
         self._alloc_elems = (self._tail_off + MAILBOX_BYTES + item - 1) // item
         self._xchg_step = 0         # never reset: the mailbox slots are addressed by it
         self._calls_on_shard = 0    # SpMVs issued on the current shard (reset() keeps the matrix)
-        if host_ops is None:
-            if not torch.cuda.is_available():
-                raise RuntimeError("PowerIteration needs a CUDA device; there is no CPU path")
-            dev = "cuda"
-            if self.exchange == "auto" and shard.world <= 4:
-                # measured on R-MAT scale 27: peer stores win at 2 and 4 GPUs (8.15 / 4.30 ms per
-                # step vs 8.43 / 4.42 with multicast), multicast wins at 8 (2.32 vs 2.94 ms)
-                self.exchange = "p2p"
-            if self.exchange in ("mc", "auto"):
-                try:
-                    self._alloc_symmetric()
-                    self.exchange = "mc"
-                except Exception as e:  # no symmetric memory / no NVLS here
-                    self.exchange_note = f"multicast unavailable ({type(e).__name__}: {e}); "
-                    self.exchange = "p2p"
-                    self._symm, self.xbuf, self._full = [], [], []
-            if self.exchange != "mc":
-                self._raw = [_RawDeviceArray(self._alloc_elems, self.dtype) for _ in range(2)]
-                self._full = [r.tensor() for r in self._raw]
-                self.xbuf = [t[:self.n] for t in self._full]
-            if self.exchange == "p2p":
-                try:
-                    self._map_peers()
-                except Exception as e:  # no IPC / no peer access: fall back to NCCL, and say so
-                    self.exchange = "nccl"
-                    self.exchange_note += f"p2p unavailable ({type(e).__name__}: {e}); nccl all-gather"
-        else:
-            self.xbuf = [torch.zeros(self.n, dtype=self.dtype) for _ in range(2)]
-            dev = "cpu"
-            if self.exchange != "none":
-                self.exchange = "nccl"  # collectives only on the host
+        dev = self._setup_buffers()
         self._local_events = None   # set by shard_local_ms: (start, stop) events per step
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
         self.alpha = torch.ones(1, dtype=self.dtype, device=dev)
         self.step_no = 0
         # the norm exchange kernel replaces sum of squares + all-reduce + 1/sqrt wherever the
         # mailboxes are mapped into the peers (always on one GPU); "nccl" keeps the collective
-        self.fused_norm = host_ops is None and self.exchange in ("none", "p2p", "mc")
+        self.fused_norm = dev == "cuda" and self.exchange in ("none", "p2p", "mc")
         if self.fused_norm:
             self._init_mailbox()
         self.reset()
 
     # ------------------------------------------------------------------ setup
+    def _setup_buffers(self) -> str:
+        """Allocate the two replicas of x and map them into the peers; returns the device."""
+        shard = self.shard
+        if not torch.cuda.is_available():
+            raise RuntimeError("PowerIteration needs a CUDA device; there is no CPU path")
+        dev = "cuda"
+        if self.exchange == "auto" and shard.world <= 4:
+            # measured on R-MAT scale 27: peer stores win at 2 and 4 GPUs (8.15 / 4.30 ms per
+            # step vs 8.43 / 4.42 with multicast), multicast wins at 8 (2.32 vs 2.94 ms)
+            self.exchange = "p2p"
+        if self.exchange in ("mc", "auto"):
+            try:
+                self._alloc_symmetric()
+                self.exchange = "mc"
+            except Exception as e:  # no symmetric memory / no NVLS here
+                self.exchange_note = f"multicast unavailable ({type(e).__name__}: {e}); "
+                self.exchange = "p2p"
+                self._symm, self.xbuf, self._full = [], [], []
+        if self.exchange != "mc":
+            self._raw = [_RawDeviceArray(self._alloc_elems, self.dtype) for _ in range(2)]
+            self._full = [r.tensor() for r in self._raw]
+            self.xbuf = [t[:self.n] for t in self._full]
+        if self.exchange == "p2p":
+            try:
+                self._map_peers()
+            except Exception as e:  # no IPC / no peer access: fall back to NCCL, and say so
+                self.exchange = "nccl"
+                self.exchange_note += f"p2p unavailable ({type(e).__name__}: {e}); nccl all-gather"
+        return dev
+
+    def _sync(self):
+        torch.cuda.synchronize()
+
+    def _local_spmv(self, x, y, peers):
+        """y = alpha * A_local x, fanned out to the peers' replicas."""
+        m = self.shard.csr
+        # the shard never changes between steps: from its second SpMV on, what earlier calls
+        # derived from it (tile coordinates, the hot-x plan) is reused
+        spmv_mod.spmv_ex(self.kind, m.Ap, m.Aj, m.Ax, x, y, n_cols=self.n, alpha_dev=self.alpha,
+                         y_peers=peers, multicast=self.exchange == "mc",
+                         static_pattern=self._calls_on_shard > 0)
+        self._calls_on_shard += 1
+
+    def _local_sumsq(self, y):
+        st = _lib.lib().spmvb200_sum_squares(self.vbits, y.numel(), y.data_ptr(), self.sumsq.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream)
+        _lib.check(st, "spmvb200_sum_squares")
+
+    def _alpha_from_sumsq(self):
+        st = _lib.lib().spmvb200_inv_sqrt(self.vbits, self.sumsq.data_ptr(), self.alpha.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream)
+        _lib.check(st, "spmvb200_inv_sqrt")
+
     def _alloc_symmetric(self):
         """x replicas in torch symmetric memory: every rank allocates the same buffers, the
         rendezvous maps them into one NVLink multicast object (NVLS), and a single
@@ -264,8 +287,7 @@ class PowerIteration:
         self.xbuf[1].zero_()
         self.alpha.fill_(1.0)
         self.step_no = 0
-        if self.host_ops is None:
-            torch.cuda.synchronize()
+        self._sync()
         if self.world > 1:
             self.dist.barrier(group=self.group)
 
@@ -282,42 +304,30 @@ class PowerIteration:
             peers = [p + s.row_begin * item for p in self.peer_ptrs[nxt]]
         else:
             peers = []
-        if self.host_ops is None:
-            if self._local_events is not None:
-                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-                self._local_events.append(ev)
-                ev[0].record()
-            # the shard never changes between steps: from its second SpMV on, what earlier calls
-            # derived from it (tile coordinates, the hot-x plan) is reused
-            spmv_mod.spmv_ex(self.kind, m.Ap, m.Aj, m.Ax, x, y, n_cols=self.n, alpha_dev=self.alpha,
-                             y_peers=peers, multicast=self.exchange == "mc",
-                             static_pattern=self._calls_on_shard > 0)
-            self._calls_on_shard += 1
-            if self.step_no == 0 and self.exchange in ("p2p", "mc"):
-                # The kernels send only rows that have nonzeros to the peers; an empty row's
-                # entry must therefore already be 0 in every replica.  Buffer 1 starts zeroed;
-                # buffer 0 held x0 and is cleared here, after this step's kernel has read it
-                # and before the step barrier lets any peer store into it.
-                self.xbuf[0].zero_()
-            L = _lib.lib()
-            if self.fused_norm and self._local_events is None:
-                # sum of squares, exchange of the per-rank sums, alpha and the step barrier: one kernel
-                st = L.spmvb200_norm_exchange(
-                    self.vbits, y.numel(), y.data_ptr(), self.rank, self.world, self._xchg_step,
-                    self._mailbox, self._mailbox_of_rank, self._mailbox_mc or None, self.sumsq.data_ptr(),
-                    self.alpha.data_ptr(), self.xchg_error.data_ptr(), torch.cuda.current_stream().cuda_stream)
-                _lib.check(st, "spmvb200_norm_exchange")
-                self._xchg_step += 1
-                self.step_no += 1
-                return
-            st = L.spmvb200_sum_squares(self.vbits, y.numel(), y.data_ptr(), self.sumsq.data_ptr(),
-                                        torch.cuda.current_stream().cuda_stream)
-            _lib.check(st, "spmvb200_sum_squares")
-            if self._local_events is not None:
-                self._local_events[-1][1].record()
-        else:
-            self.host_ops.spmv(m, x, y, self.alpha)
-            self.sumsq[0] = (y.double() ** 2).sum()
+        if self._local_events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self._local_events.append(ev)
+            ev[0].record()
+        self._local_spmv(x, y, peers)
+        if self.step_no == 0 and self.exchange in ("p2p", "mc"):
+            # The kernels send only rows that have nonzeros to the peers; an empty row's
+            # entry must therefore already be 0 in every replica.  Buffer 1 starts zeroed;
+            # buffer 0 held x0 and is cleared here, after this step's kernel has read it
+            # and before the step barrier lets any peer store into it.
+            self.xbuf[0].zero_()
+        if self.fused_norm and self._local_events is None:
+            # sum of squares, exchange of the per-rank sums, alpha and the step barrier: one kernel
+            st = _lib.lib().spmvb200_norm_exchange(
+                self.vbits, y.numel(), y.data_ptr(), self.rank, self.world, self._xchg_step,
+                self._mailbox, self._mailbox_of_rank, self._mailbox_mc or None, self.sumsq.data_ptr(),
+                self.alpha.data_ptr(), self.xchg_error.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            _lib.check(st, "spmvb200_norm_exchange")
+            self._xchg_step += 1
+            self.step_no += 1
+            return
+        self._local_sumsq(y)
+        if self._local_events is not None:
+            self._local_events[-1][1].record()
         if self.world > 1:
             if self.exchange == "nccl":
                 views = [self.xbuf[nxt][s.row_bounds[q]:s.row_bounds[q + 1]] for q in range(self.world)]
@@ -329,13 +339,7 @@ class PowerIteration:
                         self.dist.broadcast(views[q], src=q, group=self.group)
             # the norm all-reduce is also the step barrier for the peer stores
             self.dist.all_reduce(self.sumsq, group=self.group)
-        if self.host_ops is None:
-            st = L.spmvb200_inv_sqrt(self.vbits, self.sumsq.data_ptr(), self.alpha.data_ptr(),
-                                     torch.cuda.current_stream().cuda_stream)
-            _lib.check(st, "spmvb200_inv_sqrt")
-        else:
-            s2 = float(self.sumsq[0])
-            self.alpha[0] = 1.0 / (s2 ** 0.5) if s2 > 0 else 1.0
+        self._alpha_from_sumsq()
         self.step_no += 1
 
     # ------------------------------------------------------------------ re-balancing
@@ -393,9 +397,8 @@ class PowerIteration:
         return float(self.sumsq.item()) ** 0.5
 
     def close(self):
-        if self.host_ops is None:
-            torch.cuda.synchronize()
-            self.check_exchange()
+        self._sync()
+        self.check_exchange()
         if self.world > 1:
             self.dist.barrier(group=self.group)
         for b in range(2):

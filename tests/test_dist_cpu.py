@@ -1,8 +1,9 @@
 """CPU suite, world_size 2 over gloo: the exchange protocol of the row-sharded power iteration
 (spmv_samples_b200/dist.py) -- nnz-balanced row split, double-buffered x, uneven all-gather,
 norm all-reduce as the step barrier, lagged device-style alpha -- gives the same iterates as
-the single-process iteration.  The SpMV itself is stubbed with the CPU oracle through the
-documented test hook (host_ops); the CUDA kernels are covered by the -m gpu suite."""
+the single-process iteration.  The four device operations of a step are replaced by the CPU
+oracle in a subclass that lives HERE (HostProtocolIteration): the product class has no host
+arithmetic and no hook for any; the CUDA kernels are covered by the -m gpu suite."""
 import os
 import socket
 
@@ -17,12 +18,31 @@ from spmv_samples_b200 import generate
 from spmv_samples_b200.dist import PowerIteration, Shard
 
 
-class OracleOps:
-    """y = alpha * A_local x with the CPU oracle (cpu_navie.hpp:3-17)."""
+class HostProtocolIteration(PowerIteration):
+    """PowerIteration with its device operations replaced by the CPU oracle (cpu_navie.hpp:3-17)
+    and CPU tensors, so that the exchange protocol runs over gloo.  Test infrastructure."""
 
-    def spmv(self, csr, x, y, alpha):
+    def _setup_buffers(self):
+        self.xbuf = [torch.zeros(self.n, dtype=self.dtype) for _ in range(2)]
+        self._full = list(self.xbuf)
+        if self.exchange != "none":
+            self.exchange = "nccl"      # the collective path; there is nothing to map into peers
+        return "cpu"
+
+    def _sync(self):
+        pass
+
+    def _local_spmv(self, x, y, peers):
+        csr = self.shard.csr
         out = cpu.spmv(csr.Ap.numpy(), csr.Aj.numpy(), csr.Ax.numpy(), x.numpy())
-        y.copy_(torch.from_numpy(out * np.float32(alpha.item())))
+        y.copy_(torch.from_numpy(out * np.float32(self.alpha.item())))
+
+    def _local_sumsq(self, y):
+        self.sumsq[0] = (y.double() ** 2).sum()
+
+    def _alpha_from_sumsq(self):
+        s2 = float(self.sumsq[0])
+        self.alpha[0] = 1.0 / (s2 ** 0.5) if s2 > 0 else 1.0
 
 
 def make_shard(Ap, Aj, Ax, rank, world):
@@ -49,7 +69,7 @@ def _worker(rank, world, port, steps, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     Ap, Aj, Ax = g.rmat(10, 16, 7)
     shard = make_shard(Ap, Aj, Ax, rank, world)
-    it = PowerIteration(shard, Ap.shape[0] - 1, exchange="nccl", host_ops=OracleOps())
+    it = HostProtocolIteration(shard, Ap.shape[0] - 1, exchange="nccl")
     assert it.exchange == "nccl"
     for _ in range(steps):
         it.step()
