@@ -251,7 +251,9 @@ SPMVB200_API int spmvb200_gather_yardstick(int64_t x_elements, int64_t gathers, 
  * array x_hot (refilled from x before every SpMV).  Products and their order are unchanged: y is
  * bit-identical.  Costs nnz * 4 bytes of device memory, built at the first flagged call.  Reports
  * what was built for this Aj on the current device (0 columns = no plan).  The flag therefore
- * vouches for Aj as well as Ap.  Nothing in the reference corresponds (it gathers x[Aj[k]] as is,
+ * vouches for Aj as well as Ap.  Callers behind the reference's SpMV(kind_str, ...) signature,
+ * which has no flags, vouch through option "assume_static_pattern" = 1 (main.cu does for its
+ * timing loop).  Nothing in the reference corresponds (it gathers x[Aj[k]] as is,
  * merge_based/agent_spmv_orig.cuh:474-506). */
 SPMVB200_API int spmvb200_hot_x_info(const int32_t *Aj, int64_t *hot_columns, double *hot_share,
                                      double *build_ms);
@@ -363,6 +365,11 @@ SPMVB200_API int spmvb200_power_steps(spmvb200_power_t *p, int steps);
 SPMVB200_API int spmvb200_power_run(spmvb200_power_t *p, int steps, double *ms_per_step);
 SPMVB200_API int spmvb200_power_sync(spmvb200_power_t *p);
 SPMVB200_API int spmvb200_power_get(spmvb200_power_t *p, void *x_host, double *norm, int64_t *row_bounds);
+/* 0: the replicas of x are fed by peer stores (or there is one GPU); 1: by one multimem.st per row
+ * through an NVLink multicast object (csrc/mcast.cu).  Option "power_exchange": 0 / 1 force one
+ * (1 fails with SPMVB200_ERR_UNSUPPORTED where there is no multicast), -1 = multicast above 4 GPUs
+ * where available. */
+SPMVB200_API int spmvb200_power_exchange(const spmvb200_power_t *p);
 SPMVB200_API void spmvb200_power_destroy(spmvb200_power_t *p);
 
 /* ---- device timing of the dominant kernel (bench.py's roofline.achieved) ------------------

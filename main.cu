@@ -16,6 +16,8 @@
 //   * the host CSR loop is timed too (one thread, like the reference's), as a reported baseline.
 // Options: --iters N (default 2000, reference/main.cu:19)   --x ones|random (default ones,
 //   reference/main.cu:41)   --flush (evict L2 between timed calls)   --peak GBps
+//   --dynamic-pattern: the timing loop does not declare the matrix unchanged between calls (the
+//   default does, through option "assume_static_pattern": partition and hot-x plan are reused)
 //   --power K [--gpus N]: K power-iteration steps, the matrix row-sharded over N GPUs of the box
 //   (one process, peer access; csrc/multi.cu) -- the multi-GPU configuration without Python
 #include <algorithm>
@@ -46,6 +48,7 @@ struct Options {
     int iters = TEST_TIMES;
     bool random_x = false;
     bool flush = false;
+    bool static_pattern = true;  // --dynamic-pattern: do not vouch for an unchanged matrix in the timing loop
     double peak_gbs = 6452.2;  // fallback: this pool's measured copy bandwidth; MEASURED_PEAKS.json beside
                                // the working directory, or --peak, overrides it
     double datasheet_gbs = 8000.0;
@@ -126,9 +129,14 @@ static int run(const Options &opt, const string &name, index_t n_rows, index_t n
     // calls are queued back to back, as in reference/main.cu:104-110, inside ONE event pair and
     // the host synchronises once after the loop: no launch latency or idle gap between calls is
     // counted as kernel time, and none is hidden either.
-    printf("Time cost (%d calls%s; %.0f algorithmic bytes, %.0f flops per call):\n", opt.iters,
+    // The timing loop calls every kind on one unchanged matrix, which the SpMV(kind_str, ...)
+    // signature cannot say: the driver says it through a library option, so that the calls may
+    // reuse the merge-path partition and the hot-x plan (spmv_b200.h, SPMVB200_FLAG_STATIC_PATTERN).
+    // The check above ran without it.
+    checkSpmvStatus(spmvb200_set_option("assume_static_pattern", opt.static_pattern ? 1 : 0));
+    printf("Time cost (%d calls%s%s; %.0f algorithmic bytes, %.0f flops per call):\n", opt.iters,
            opt.flush ? ", L2 flushed before each, timed one by one" : ", queued back to back, timed as one interval",
-           bytes, flops);
+           opt.static_pattern ? ", matrix declared unchanged between calls" : "", bytes, flops);
     cudaEvent_t loop_begin, loop_end;
     checkCudaErr(cudaEventCreate(&loop_begin));
     checkCudaErr(cudaEventCreate(&loop_end));
@@ -163,6 +171,7 @@ static int run(const Options &opt, const string &name, index_t n_rows, index_t n
     printf("[%-12s] %.3f ms for %.0f nonzeros on 1 host thread: %.2f GFLOP/s (reported baseline)\n",
            "cpu fp64", cpu_s * 1e3, checked_nnz, 2.0 * checked_nnz / cpu_s / 1e9);
 
+    checkSpmvStatus(spmvb200_set_option("assume_static_pattern", 0));
     checkCudaErr(cudaEventDestroy(loop_begin));
     checkCudaErr(cudaEventDestroy(loop_end));
     //--------------------------------------------------------------------------
@@ -180,7 +189,8 @@ static int run(const Options &opt, const string &name, index_t n_rows, index_t n
         checkSpmvStatus(spmvb200_power_run(pw, opt.power, &ms));
         vector<int64_t> rb((size_t)opt.gpus + 1);
         checkSpmvStatus(spmvb200_power_get(pw, nullptr, &norm, rb.data()));
-        printf("Power iteration (%d steps, %d GPU%s, kind auto):\n", opt.power, opt.gpus, opt.gpus > 1 ? "s" : "");
+        printf("Power iteration (%d steps, %d GPU%s, kind auto%s):\n", opt.power, opt.gpus, opt.gpus > 1 ? "s" : "",
+               opt.gpus < 2 ? "" : spmvb200_power_exchange(pw) ? ", rows exchanged by NVLink multicast stores" : ", rows exchanged by peer stores");
         printf("[%-12s] %12lf ms/step  %9.1f GFLOP/s  %8.1f GB/s  %5.1f%% of measured %.0f GB/s x %d  ||A x|| = %.9g\n",
                "power", ms, flops / (ms * 1e-3) / 1e9, bytes / (ms * 1e-3) / 1e9,
                100.0 * bytes / (ms * 1e-3) / 1e9 / (opt.peak_gbs * opt.gpus), opt.peak_gbs, opt.gpus, norm);
@@ -280,7 +290,7 @@ static int run_synthetic(const Options &opt, const string &cfg, long size) {
 int main(int argc, char **argv) {
     if (argc < 3) {
         cerr << "usage: ./bin/<program-name>  <filename.mtx | synthetic:c1..c5[:size]>  <SpMV_kind_string>..."
-                "  [--iters N] [--x ones|random] [--flush] [--peak GB/s] [--power K [--gpus N]]"
+                "  [--iters N] [--x ones|random] [--flush] [--dynamic-pattern] [--peak GB/s] [--power K [--gpus N]]"
              << endl;
         exit(1);
     }
@@ -291,6 +301,7 @@ int main(int argc, char **argv) {
         if (a == "--iters" && i + 1 < argc) opt.iters = atoi(argv[++i]);
         else if (a == "--x" && i + 1 < argc) opt.random_x = string(argv[++i]) == "random";
         else if (a == "--flush") opt.flush = true;
+        else if (a == "--dynamic-pattern") opt.static_pattern = false;
         else if (a == "--peak" && i + 1 < argc) opt.peak_gbs = atof(argv[++i]);
         else if (a == "--gpus" && i + 1 < argc) opt.gpus = atoi(argv[++i]);
         else if (a == "--power" && i + 1 < argc) opt.power = atoi(argv[++i]);

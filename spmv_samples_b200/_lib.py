@@ -133,6 +133,7 @@ def lib() -> C.CDLL:
     L.spmvb200_power_sync.argtypes = [C.c_void_p]
     L.spmvb200_power_get.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.spmvb200_power_destroy.argtypes = [C.c_void_p]
+    L.spmvb200_power_exchange.argtypes = [C.c_void_p]
     L.spmvb200_power_destroy.restype = None
     L.spmvb200_norm_exchange.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_uint64,
                                          C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p,

@@ -71,7 +71,9 @@ int run(int kind, int64_t n_rows, int64_t n_cols, int64_t nnz, const void *Ap, c
     p.peers.n = n_peers;
     for (int i = 0; i < kMaxPeers; ++i) p.peers.ptr[i] = i < (n_peers < 0 ? 1 : n_peers) ? y_peers[i] : nullptr;
     p.stream = stream;
-    p.reuse_partition = (flags & SPMVB200_FLAG_STATIC_PATTERN) != 0;
+    // option "assume_static_pattern": the vouching of SPMVB200_FLAG_STATIC_PATTERN for callers whose
+    // call has no flags argument (the reference's SpMV(kind_str, ...) plugin surface)
+    p.reuse_partition = (flags & SPMVB200_FLAG_STATIC_PATTERN) != 0 || option_get("assume_static_pattern", 0) != 0;
 
     if (semiring != SPMVB200_SEMIRING_PLUS_TIMES || beta_dev) {
         // the generalised form lives in the merge-path kernel only (as in the reference)

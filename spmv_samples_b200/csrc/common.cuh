@@ -359,4 +359,10 @@ __device__ __forceinline__ void store_y_nonempty(ValT *y, const PeerOut &peers, 
 }
 #endif  // __CUDACC__
 
+// ---- mcast.cu: device memory replicated over the GPUs of this process behind one NVLink
+// multicast address (NVLS).  SPMVB200_ERR_UNSUPPORTED without multicast support.
+struct McastArena;
+int mcast_arena_create(const int *devices, int n, size_t bytes, McastArena **out, void **replica, void **mc);
+void mcast_arena_destroy(McastArena *a);
+
 }  // namespace spmvb200

@@ -40,6 +40,10 @@ struct spmvb200_power {
     int64_t n = 0, nnz = 0;
     size_t tail_off = 0;  // bytes from a replica's base to its mailbox
     uint64_t step = 0;
+    // NVLink multicast (mcast.cu): when set, the replicas of x live in its arena and mc_buf[b] is
+    // the multicast address of buffer b; otherwise they are cudaMalloc'ed and fed by peer stores
+    spmvb200::McastArena *mc = nullptr;
+    void *mc_buf[2] = {nullptr, nullptr};
 };
 
 namespace spmvb200 {
@@ -88,12 +92,16 @@ void spmvb200_power_destroy(spmvb200_power_t *p) {
         if (g.dev < 0 || cudaSetDevice(g.dev) != cudaSuccess) continue;
         if (g.stream) cudaStreamSynchronize(g.stream);
         if (g.Aj) hot_plan_drop(g.Aj);
-        for (void *q : {g.Ap, (void *)g.Aj, g.Ax, g.xbuf[0], g.xbuf[1], (void *)g.sumsq, g.alpha, (void *)g.error})
+        for (void *q : {g.Ap, (void *)g.Aj, g.Ax, (void *)g.sumsq, g.alpha, (void *)g.error})
             if (q) cudaFree(q);
+        if (!p->mc)
+            for (void *q : g.xbuf)
+                if (q) cudaFree(q);
         if (g.ev0) cudaEventDestroy(g.ev0);
         if (g.ev1) cudaEventDestroy(g.ev1);
         if (g.stream) cudaStreamDestroy(g.stream);
     }
+    mcast_arena_destroy(p->mc);
     delete p;
 }
 
@@ -207,12 +215,39 @@ int spmvb200_power_create_from_device(int n_gpus, const int *devices, int offset
             rebase_offsets_kernel<int64_t><<<grid, 256, 0, G.stream>>>(G.rows + 1, k0, static_cast<int64_t *>(G.Ap));
         count_launch();
         POWER_TRY(cudaGetLastError());
-        for (int b = 0; b < 2; ++b) POWER_TRY(cudaMalloc(&G.xbuf[b], p->tail_off + SPMVB200_MAILBOX_BYTES));
         POWER_TRY(cudaMalloc((void **)&G.sumsq, sizeof(double)));
         POWER_TRY(cudaMalloc(&G.alpha, 8));
         POWER_TRY(cudaMalloc((void **)&G.error, sizeof(int)));
         POWER_TRY(cudaMemsetAsync(G.error, 0, sizeof(int), G.stream));
     }
+    // ---- the replicas of x.  Option "power_exchange": 0 = peer stores, 1 = NVLink multicast,
+    // -1 = multicast above 4 GPUs: rows are split by nonzeros, so on a skewed matrix one GPU owns
+    // most of the rows and with peer stores sends them n_gpus - 1 times; at 8 GPUs that transfer
+    // outlasts its SpMV (mcast.cu), at 2 and 4 it hides behind it and the plain stores are cheaper.
+    const size_t stride = p->tail_off + SPMVB200_MAILBOX_BYTES;
+    const int64_t xopt = option_get("power_exchange", -1);
+    if (n_gpus > 1 && (xopt > 0 || (xopt < 0 && n_gpus > 4))) {
+        std::vector<int> devs((size_t)n_gpus);
+        std::vector<void *> base((size_t)n_gpus, nullptr);
+        for (int g = 0; g < n_gpus; ++g) devs[(size_t)g] = p->gpu[(size_t)g].dev;
+        void *mc_base = nullptr;
+        status = mcast_arena_create(devs.data(), n_gpus, 2 * stride, &p->mc, base.data(), &mc_base);
+        if (status == SPMVB200_OK) {
+            for (int b = 0; b < 2; ++b) {
+                p->mc_buf[b] = static_cast<char *>(mc_base) + (size_t)b * stride;
+                for (int g = 0; g < n_gpus; ++g)
+                    p->gpu[(size_t)g].xbuf[b] = static_cast<char *>(base[(size_t)g]) + (size_t)b * stride;
+            }
+        } else if (status != SPMVB200_ERR_UNSUPPORTED || xopt > 0) {
+            spmvb200_power_destroy(p);   // asked for by option and not available, or a real failure
+            return status;
+        }
+    }
+    if (!p->mc)
+        for (auto &G : p->gpu) {
+            POWER_TRY(cudaSetDevice(G.dev));
+            for (int b = 0; b < 2; ++b) POWER_TRY(cudaMalloc(&G.xbuf[b], stride));
+        }
     *out = p;
     status = spmvb200_power_reset(p);
     if (status != SPMVB200_OK) {
@@ -303,7 +338,12 @@ int spmvb200_power_steps(spmvb200_power_t *p, int steps) {
             int np = 0;
             for (int q = 0; q < P; ++q) {
                 mailboxes[q] = static_cast<char *>(p->gpu[(size_t)q].xbuf[0]) + p->tail_off;
-                if (q != g) peers[np++] = static_cast<char *>(p->gpu[(size_t)q].xbuf[nxt]) + (size_t)G.row_begin * vb;
+                if (q != g && !p->mc)
+                    peers[np++] = static_cast<char *>(p->gpu[(size_t)q].xbuf[nxt]) + (size_t)G.row_begin * vb;
+            }
+            if (p->mc) {   // one multimem.st per row, replicated by the switch (spmv_b200.h: n_peers == -1)
+                peers[0] = static_cast<char *>(p->mc_buf[nxt]) + (size_t)G.row_begin * vb;
+                np = -1;
             }
             spmvb200_args_t a;
             std::memset(&a, 0, sizeof(a));
@@ -330,7 +370,8 @@ int spmvb200_power_steps(spmvb200_power_t *p, int steps) {
             // in every replica: buffer 1 starts zeroed; buffer 0 held x0 and is cleared after the
             // first step's kernel has read it and before the exchange lets a peer store into it.
             if (p->step == 0 && P > 1) SPMV_CUDA_TRY(cudaMemsetAsync(G.xbuf[0], 0, (size_t)p->n * vb, G.stream));
-            SPMV_TRY(spmvb200_norm_exchange(p->value_bits, G.rows, a.y, g, P, p->step, mailboxes[g], mailboxes, nullptr,
+            SPMV_TRY(spmvb200_norm_exchange(p->value_bits, G.rows, a.y, g, P, p->step, mailboxes[g], mailboxes,
+                                            p->mc ? static_cast<char *>(p->mc_buf[0]) + p->tail_off : nullptr,
                                             G.sumsq, G.alpha, G.error, G.stream));
         }
     }
@@ -366,6 +407,9 @@ int spmvb200_power_run(spmvb200_power_t *p, int steps, double *ms_per_step) {
     if (ms_per_step) *ms_per_step = worst / steps;
     return SPMVB200_OK;
 }
+
+// how the replicas of x are fed: 0 = peer stores (or one GPU), 1 = NVLink multicast
+int spmvb200_power_exchange(const spmvb200_power_t *p) { return p && p->mc ? 1 : 0; }
 
 // the current iterate (n values, not yet scaled by 1/||.||) and ||A x_k|| of the last step
 int spmvb200_power_get(spmvb200_power_t *p, void *x_host, double *norm, int64_t *row_bounds) {

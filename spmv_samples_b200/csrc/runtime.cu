@@ -58,10 +58,12 @@ std::map<std::string, int64_t> &options() {
                                  // passes SPMVB200_FLAG_STATIC_PATTERN and x is longer than
                                  // "hot_x_min_bytes"; 0 = never; 1 = always (plan keyed on the Aj pointer)
         {"hot_x_min_bytes", 256ll << 20},
+        {"assume_static_pattern", 0},  // 1: every call is treated as carrying SPMVB200_FLAG_STATIC_PATTERN
         {"side_stream", 0},      // 1: small kernels a big one depends on (partition, x_hot refill) run on a side
                                  // stream forked / joined with events (measured: no gain outside the profiler)
         {"hot_x_fill", 0},       // how x_hot is refilled: 0/1 = gather x[hot_cols[r]], 2 = sweep over x, 3 = not at all (experiments)
         {"hot_x_max_bytes", 32ll << 20},   // size of the dense copy of the hot columns' x
+        {"power_exchange", -1},    // spmvb200_power_*: 0 = peer stores, 1 = NVLink multicast, -1 = multicast above 4 GPUs
         {"stream_ctas_per_sm", 3},  // persistent CTAs per SM of the CSR-stream kernel
         {"cusparse_alg", 0},     // 0: CUSPARSE_SPMV_ALG_DEFAULT (the reference's call), 1: CSR_ALG1, 2: CSR_ALG2
     };

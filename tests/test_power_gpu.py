@@ -349,6 +349,7 @@ def _native_power(n_gpus, Ap, Aj, Ax, steps, from_device=False, kind=3):
         norm = C.c_double()
         rb = (C.c_int64 * (n_gpus + 1))()
         _lib.check(L.spmvb200_power_get(h, x.ctypes.data, C.byref(norm), rb), "spmvb200_power_get")
+        _native_power.exchange = int(L.spmvb200_power_exchange(h))
         # a second run after reset reproduces the first bit for bit
         _lib.check(L.spmvb200_power_reset(h), "spmvb200_power_reset")
         _lib.check(L.spmvb200_power_steps(h, steps), "spmvb200_power_steps")
@@ -382,14 +383,27 @@ def test_native_power_iteration_one_gpu(off, from_device):
     assert rb == [0, Ap.shape[0] - 1] and ms > 0
 
 
+@pytest.mark.parametrize("exchange", ["peer_stores", "multicast"])
 @pytest.mark.parametrize("n_gpus", [2, 4, 8])
-def test_native_power_iteration_multi_gpu(n_gpus):
-    """Row blocks on n_gpus GPUs of this process, fused peer-store exchange, mailbox norm exchange:
-    same iterates as the oracle recurrence, row split bit-exact against the oracle's merge path."""
+def test_native_power_iteration_multi_gpu(n_gpus, exchange):
+    """Row blocks on n_gpus GPUs of this process, the exchange fused into the SpMV's row stores
+    (peer stores, or one multimem.st through an NVLink multicast object: csrc/mcast.cu), mailbox
+    norm exchange: same iterates as the oracle recurrence, row split bit-exact against the
+    oracle's merge path."""
+    from spmv_samples_b200 import spmv
     if torch.cuda.device_count() < n_gpus:
         pytest.skip(f"needs {n_gpus} GPUs")
     Ap, Aj, Ax = g.rmat(14, 16, 7, offset_dtype=np.int64)
-    x, norm, rb, ms = _native_power(n_gpus, Ap, Aj, Ax, 6)
+    spmv.set_option("power_exchange", 1 if exchange == "multicast" else 0)
+    try:
+        x, norm, rb, ms = _native_power(n_gpus, Ap, Aj, Ax, 6)
+    except RuntimeError as e:
+        if exchange == "multicast" and getattr(e, "status", 0) == 4:   # SPMVB200_ERR_UNSUPPORTED
+            pytest.skip("no NVLink multicast on this box")
+        raise
+    finally:
+        spmv.set_option("power_exchange", -1)
+    assert _native_power.exchange == (1 if exchange == "multicast" else 0)
     assert rb == cpu.row_split(Ap, n_gpus).tolist()
     ref = _oracle_power(Ap, Aj, Ax, 6)
     assert np.linalg.norm(x.astype(np.float64) - ref) <= 1e-4 * np.linalg.norm(ref)
