@@ -367,8 +367,8 @@ SPMVB200_API int spmvb200_power_sync(spmvb200_power_t *p);
 SPMVB200_API int spmvb200_power_get(spmvb200_power_t *p, void *x_host, double *norm, int64_t *row_bounds);
 /* 0: the replicas of x are fed by peer stores (or there is one GPU); 1: by one multimem.st per row
  * through an NVLink multicast object (csrc/mcast.cu).  Option "power_exchange": 0 / 1 force one
- * (1 fails with SPMVB200_ERR_UNSUPPORTED where there is no multicast), -1 = multicast above 4 GPUs
- * where available. */
+ * (1 fails with SPMVB200_ERR_UNSUPPORTED where there is no multicast), -1 = multicast where the
+ * box has it, peer stores otherwise. */
 SPMVB200_API int spmvb200_power_exchange(const spmvb200_power_t *p);
 SPMVB200_API void spmvb200_power_destroy(spmvb200_power_t *p);
 

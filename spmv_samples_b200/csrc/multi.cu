@@ -221,12 +221,13 @@ int spmvb200_power_create_from_device(int n_gpus, const int *devices, int offset
         POWER_TRY(cudaMemsetAsync(G.error, 0, sizeof(int), G.stream));
     }
     // ---- the replicas of x.  Option "power_exchange": 0 = peer stores, 1 = NVLink multicast,
-    // -1 = multicast above 4 GPUs: rows are split by nonzeros, so on a skewed matrix one GPU owns
-    // most of the rows and with peer stores sends them n_gpus - 1 times; at 8 GPUs that transfer
-    // outlasts its SpMV (mcast.cu), at 2 and 4 it hides behind it and the plain stores are cheaper.
+    // -1 = multicast where the box has it.  Rows are split by nonzeros, so on a skewed matrix one
+    // GPU owns most of the rows and with peer stores sends them n_gpus - 1 times; at 8 GPUs that
+    // transfer outlasts its SpMV (mcast.cu).  R-MAT scale 27, ms per step at 2 / 4 / 8 GPUs:
+    // 5.71 / 2.93 / 1.60 with multicast, 5.88 / 3.09 / 2.63 with peer stores.
     const size_t stride = p->tail_off + SPMVB200_MAILBOX_BYTES;
     const int64_t xopt = option_get("power_exchange", -1);
-    if (n_gpus > 1 && (xopt > 0 || (xopt < 0 && n_gpus > 4))) {
+    if (n_gpus > 1 && xopt != 0) {
         std::vector<int> devs((size_t)n_gpus);
         std::vector<void *> base((size_t)n_gpus, nullptr);
         for (int g = 0; g < n_gpus; ++g) devs[(size_t)g] = p->gpu[(size_t)g].dev;

@@ -63,7 +63,7 @@ std::map<std::string, int64_t> &options() {
                                  // stream forked / joined with events (measured: no gain outside the profiler)
         {"hot_x_fill", 0},       // how x_hot is refilled: 0/1 = gather x[hot_cols[r]], 2 = sweep over x, 3 = not at all (experiments)
         {"hot_x_max_bytes", 32ll << 20},   // size of the dense copy of the hot columns' x
-        {"power_exchange", -1},    // spmvb200_power_*: 0 = peer stores, 1 = NVLink multicast, -1 = multicast above 4 GPUs
+        {"power_exchange", -1},    // spmvb200_power_*: 0 = peer stores, 1 = NVLink multicast, -1 = multicast where available
         {"stream_ctas_per_sm", 3},  // persistent CTAs per SM of the CSR-stream kernel
         {"cusparse_alg", 0},     // 0: CUSPARSE_SPMV_ALG_DEFAULT (the reference's call), 1: CSR_ALG1, 2: CSR_ALG2
     };

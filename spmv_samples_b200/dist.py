@@ -179,10 +179,10 @@ class PowerIteration:
         if not torch.cuda.is_available():
             raise RuntimeError("PowerIteration needs a CUDA device; there is no CPU path")
         dev = "cuda"
-        if self.exchange == "auto" and shard.world <= 4:
-            # measured on R-MAT scale 27: peer stores win at 2 and 4 GPUs (8.15 / 4.30 ms per
-            # step vs 8.43 / 4.42 with multicast), multicast wins at 8 (2.32 vs 2.94 ms)
-            self.exchange = "p2p"
+        # "auto" takes the multicast exchange at every world size and falls back to peer stores where
+        # there is no NVLS.  Measured on R-MAT scale 27 with the multicast-specialised tile kernel:
+        # 5.68 / 2.93 / 1.62 ms per step at 2 / 4 / 8 GPUs against 5.87 / 3.30 / 2.6 with peer stores
+        # (rows are split by nonzeros, so one rank owns most of the ROWS and sends them world-1 times).
         if self.exchange in ("mc", "auto"):
             try:
                 self._alloc_symmetric()
