@@ -257,6 +257,12 @@ SPMVB200_API int spmvb200_gather_yardstick(int64_t x_elements, int64_t gathers, 
  * merge_based/agent_spmv_orig.cuh:474-506). */
 SPMVB200_API int spmvb200_hot_x_info(const int32_t *Aj, int64_t *hot_columns, double *hot_share,
                                      double *build_ms);
+/* The first `table_columns` ranks of that plan are its most frequent columns: the persistent form
+ * of the merge-path tile kernel (one CTA per SM walking over tiles) keeps their x values in a
+ * shared-memory table, where a gather costs a ninth of an L1 gather (options "hot_x_table",
+ * "hot_x_table_bytes").  With it the plan is also built for a short x (then all hot columns are
+ * table columns).  table_share: the fraction of the gathers they receive. */
+SPMVB200_API int spmvb200_hot_x_table_info(const int32_t *Aj, int64_t *table_columns, double *table_share);
 
 /* ---- host-buffer convenience: the end-to-end call --------------------------------------
  * A CSR matrix uploaded once (as reference/main.cu:55-69 does), then y = A*x with x and y

@@ -151,6 +151,7 @@ def lib() -> C.CDLL:
     L.spmvb200_ipc_close.argtypes = [C.c_void_p]
     L.spmvb200_release_cache.restype = None
     L.spmvb200_gather_yardstick.argtypes = [C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
+    L.spmvb200_hot_x_table_info.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
     L.spmvb200_hot_x_info.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double),
                                       C.POINTER(C.c_double)]
     for kind in ("merge", "vector", "light", "stream", "auto", "cusparse"):

@@ -329,6 +329,16 @@ int spmvb200_hot_x_info(const int32_t *Aj, int64_t *hot_columns, double *hot_sha
     return SPMVB200_OK;
 }
 
+int spmvb200_hot_x_table_info(const int32_t *Aj, int64_t *table_columns, double *table_share) {
+    if (table_columns) *table_columns = 0;
+    if (table_share) *table_share = 0.0;
+    if (const HotPlan *plan = hot_plan_peek(Aj)) {
+        if (table_columns) *table_columns = plan->K_table;
+        if (table_share) *table_share = plan->table_share;
+    }
+    return SPMVB200_OK;
+}
+
 }  // extern "C"
 
 // ---- host-buffer matrix object -------------------------------------------------------------

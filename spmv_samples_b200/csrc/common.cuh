@@ -53,6 +53,7 @@ int current_device_info(const DeviceInfo **out);
 
 // cudaFuncAttributePreferredSharedMemoryCarveout for `kernel` on the current device, applied
 // once per (device, kernel, value).  percent < 0 = the driver's default.
+int apply_max_dynamic_smem(const void *kernel, int64_t bytes);
 int apply_carveout(const void *kernel, int64_t percent);
 
 // Per-(device, stream) scratch that survives across calls, grown on demand.
@@ -155,15 +156,15 @@ int launch_spmm(int k, int32_t n_rows, int32_t n_cols, OffT nnz, const OffT *Ap,
 struct HotPlan {
     const int32_t *Aj2 = nullptr;
     const int32_t *hot_cols = nullptr;
-    const uint32_t *bitmap = nullptr;   // bit c % 32 of word c / 32: column c is hot
-    const uint32_t *rank32 = nullptr;   // rank of the first hot column of each word
     int64_t K = 0;
+    int64_t K_table = 0;      // ranks 0 .. K_table-1: the most frequent columns (shared-memory table class)
     int32_t n_cols = 0;
     uint32_t threshold = 0;   // a column is hot when it occurs at least this often
     double hot_share = 0.0;   // fraction of the gathers that go to hot columns
+    double table_share = 0.0; // ... and to the table class
     double build_ms = 0.0;
 };
-int hot_plan_get(const int32_t *Aj, int64_t nnz, int32_t n_cols, size_t val_bytes, cudaStream_t stream,
+int hot_plan_get(const int32_t *Aj, int64_t nnz, int32_t n_cols, int64_t k_max, int64_t k_table, cudaStream_t stream,
                  bool may_build, const HotPlan **out);
 template <typename ValT> int hot_gather(const HotPlan &plan, const ValT *x, cudaStream_t stream, const ValT **x_hot);
 void hot_plan_clear();

@@ -28,7 +28,26 @@ namespace spmvb200 {
 
 namespace {
 
-constexpr int kCountBuckets = 1026;  // bucket b < 1025: columns seen exactly b times; 1025: more
+// Occurrence counts are binned on a logarithmic scale, eight bins per octave (exact up to 15):
+// bin(n) = 8 * msb(n) + the three bits below the leading one.  "count >= lower edge of bin b" is
+// then the same set as "bin >= b", which is what a threshold needs.
+constexpr int kCountBuckets = 256;
+__host__ __device__ __forceinline__ int count_bucket(uint32_t n) {   // n >= 1
+#ifdef __CUDA_ARCH__
+    const int msb = 31 - __clz(n);
+#else
+    int msb = 0;
+    while ((n >> msb) > 1u) ++msb;
+#endif
+    const uint32_t sub = msb >= 3 ? (n >> (msb - 3)) & 7u : (n << (3 - msb)) & 7u;
+    return msb * 8 + (int)sub;
+}
+inline uint32_t bucket_lower_edge(int b) {
+    const int msb = b / 8;
+    const uint64_t m = 8u + (uint32_t)(b % 8);
+    const uint64_t e = msb >= 3 ? m << (msb - 3) : (m << msb) >> 3;
+    return e > 0xffffffffull ? 0xffffffffu : (uint32_t)e;
+}
 
 __global__ void __launch_bounds__(256)
 hot_count_kernel(const int32_t *__restrict__ Aj, int64_t nnz, uint32_t *__restrict__ counts) {
@@ -59,7 +78,8 @@ hot_hist_kernel(const uint32_t *__restrict__ counts, int64_t n_cols, unsigned lo
     __syncthreads();
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cols; c += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t n = counts[c];
-        const int b = n < (uint32_t)(kCountBuckets - 1) ? (int)n : kCountBuckets - 1;
+        if (n == 0u) continue;
+        const int b = count_bucket(n);
         atomicAdd(&s_cols[b], 1u);
         atomicAdd(&s_mass[b], (unsigned long long)n);
     }
@@ -70,22 +90,30 @@ hot_hist_kernel(const uint32_t *__restrict__ counts, int64_t n_cols, unsigned lo
     }
 }
 
-struct IsHot {
-    uint32_t threshold;
-    __host__ __device__ __forceinline__ uint32_t operator()(const uint32_t &n) const { return n >= threshold ? 1u : 0u; }
+// two classes of hot columns: count >= hi ("table": the few thousand most frequent ones, which the
+// persistent tile kernel keeps in shared memory) and lo <= count < hi
+struct InBand {
+    uint32_t lo, hi;   // lo <= n < hi; hi == 0 means no upper bound
+    __host__ __device__ __forceinline__ uint32_t operator()(const uint32_t &n) const {
+        return (n >= lo && (hi == 0u || n < hi)) ? 1u : 0u;
+    }
 };
 
-// rank[] holds the exclusive scan of the hot flags on entry and the remap table on exit
+// Ranks: the table class first (0 .. K_table-1), the other hot columns after it, both in column
+// order.  rank_t / rank_w hold the exclusive scans of the two class flags on entry; rank_t is the
+// remap table on exit (hot column -> 0x80000000 | rank, any other -> itself).
 __global__ void __launch_bounds__(256)
-hot_remap_table_kernel(const uint32_t *__restrict__ counts, int64_t n_cols, uint32_t threshold,
-                       uint32_t *__restrict__ rank, int32_t *__restrict__ hot_cols) {
+hot_remap_table_kernel(const uint32_t *__restrict__ counts, int64_t n_cols, uint32_t threshold, uint32_t table_threshold,
+                       uint32_t K_table, uint32_t *__restrict__ rank_t, const uint32_t *__restrict__ rank_w,
+                       int32_t *__restrict__ hot_cols) {
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cols; c += (int64_t)gridDim.x * blockDim.x) {
-        if (counts[c] >= threshold) {
-            const uint32_t r = rank[c];
+        const uint32_t n = counts[c];
+        if (n >= threshold) {
+            const uint32_t r = n >= table_threshold ? rank_t[c] : K_table + rank_w[c];
             hot_cols[r] = (int32_t)c;
-            rank[c] = 0x80000000u | r;
+            rank_t[c] = 0x80000000u | r;
         } else {
-            rank[c] = (uint32_t)c;
+            rank_t[c] = (uint32_t)c;
         }
     }
 }
@@ -109,29 +137,11 @@ hot_remap_kernel(const int32_t *__restrict__ Aj, int64_t nnz, const uint32_t *__
     }
 }
 
-// One warp per 32 columns: which of them are hot (a word of the bitmap) and the rank of the first
-// (the exclusive scan at the word's first column).  Runs before the remap-table kernel turns the
-// scan into the table.
-__global__ void __launch_bounds__(256)
-hot_bitmap_kernel(const uint32_t *__restrict__ counts, const uint32_t *__restrict__ rank, int64_t n_cols,
-                  uint32_t threshold, uint32_t *__restrict__ bitmap, uint32_t *__restrict__ rank32) {
-    const int lane = threadIdx.x & 31;
-    const int64_t words = (n_cols + 31) / 32;
-    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < words;
-         w += ((int64_t)gridDim.x * blockDim.x) >> 5) {
-        const int64_t c = w * 32 + lane;
-        const unsigned mask = __ballot_sync(0xffffffffu, c < n_cols && counts[c] >= threshold);
-        if (lane == 0) {
-            bitmap[w] = mask;
-            rank32[w] = rank[w * 32];
-        }
-    }
-}
-
 struct PlanEntry {
     HotPlan plan;
     int64_t nnz = 0;
     int32_t n_cols = 0;
+    int64_t k_max = 0, k_table = 0;  // what it was built for
     bool none = false;  // built and found not worth it: do not try again
 };
 using PlanKey = std::pair<int, const void *>;
@@ -141,12 +151,13 @@ std::map<PlanKey, PlanEntry> g_plans;
 void entry_free(PlanEntry &e) {
     if (e.plan.Aj2) cudaFree(const_cast<int32_t *>(e.plan.Aj2));
     if (e.plan.hot_cols) cudaFree(const_cast<int32_t *>(e.plan.hot_cols));
-    if (e.plan.bitmap) cudaFree(const_cast<uint32_t *>(e.plan.bitmap));
-    if (e.plan.rank32) cudaFree(const_cast<uint32_t *>(e.plan.rank32));
     e = PlanEntry{};
 }
 
-int build(const int32_t *Aj, int64_t nnz, int32_t n_cols, size_t val_bytes, cudaStream_t stream, PlanEntry &e) {
+// k_max: how many columns x_hot may hold; k_table: how many of them the shared-memory table of
+// the persistent tile kernel may hold (0: no table class)
+int build(const int32_t *Aj, int64_t nnz, int32_t n_cols, int64_t k_max, int64_t k_table, cudaStream_t stream,
+          PlanEntry &e) {
     const DeviceInfo *di = nullptr;
     SPMV_TRY(current_device_info(&di));
     const unsigned grid = (unsigned)di->sm_count * 8;
@@ -155,12 +166,13 @@ int build(const int32_t *Aj, int64_t nnz, int32_t n_cols, size_t val_bytes, cuda
     SPMV_CUDA_TRY(cudaEventCreate(&t1));
     SPMV_CUDA_TRY(cudaEventRecord(t0, stream));
 
-    uint32_t *counts = nullptr, *rank = nullptr;
+    uint32_t *counts = nullptr, *rank_t = nullptr, *rank_w = nullptr;
     unsigned long long *hist = nullptr;
     void *scan_tmp = nullptr;
     auto cleanup = [&]() {
         if (counts) cudaFree(counts);
-        if (rank) cudaFree(rank);
+        if (rank_t) cudaFree(rank_t);
+        if (rank_w) cudaFree(rank_w);
         if (hist) cudaFree(hist);
         if (scan_tmp) cudaFree(scan_tmp);
         if (t0) cudaEventDestroy(t0);
@@ -188,65 +200,74 @@ int build(const int32_t *Aj, int64_t nnz, int32_t n_cols, size_t val_bytes, cuda
     HOT_TRY(cudaMemcpyAsync(h, hist, sizeof(h), cudaMemcpyDeviceToHost, stream));
     HOT_TRY(cudaStreamSynchronize(stream));
 
-    // threshold: as many of the most frequent columns as fit "hot_x_max_bytes" of x_hot, a column
-    // seen once gaining nothing
-    const int64_t k_max = option_get("hot_x_max_bytes", 32 << 20) / (int64_t)val_bytes;
-    uint32_t threshold = 0;
-    int64_t K = 0;
-    unsigned long long mass = 0;
+    // thresholds: as many of the most frequent columns as fit x_hot (a column seen once gains
+    // nothing), and among them as many as fit the shared-memory table
+    uint32_t threshold = 0, table_threshold = 0;
+    int64_t K = 0, K_table = 0;
+    unsigned long long mass = 0, table_mass = 0;
     {
         int64_t cols = 0;
         unsigned long long m = 0;
-        for (int b = kCountBuckets - 1; b >= 2; --b) {
+        for (int b = kCountBuckets - 1; b >= count_bucket(2u); --b) {
             if (cols + (int64_t)h[b] > k_max) break;
             cols += (int64_t)h[b];
             m += h[kCountBuckets + b];
-            threshold = (uint32_t)b;
+            if (h[b] == 0) continue;
+            threshold = bucket_lower_edge(b);
             K = cols;
             mass = m;
+            if (cols <= k_table) {
+                table_threshold = threshold;
+                K_table = cols;
+                table_mass = m;
+            }
         }
     }
     e.nnz = nnz;
     e.n_cols = n_cols;
-    // not worth a second copy of Aj unless the hot columns take a good share of the gathers
-    if (K == 0 || (double)mass < 0.25 * (double)nnz) {
+    e.k_max = k_max;
+    e.k_table = k_table;
+    // not worth a second copy of Aj unless the hot columns take a good share of the gathers: a
+    // quarter for the dense x_hot, a tenth when all of them sit in the shared-memory table
+    if (K == 0 || (double)mass < (K == K_table ? 0.10 : 0.25) * (double)nnz) {
         cleanup();
         e.none = true;
         return SPMVB200_OK;
     }
+    if (K_table == 0) table_threshold = 0xffffffffu;
 
-    HOT_TRY(cudaMalloc(&rank, (size_t)n_cols * 4));
-    cub::TransformInputIterator<uint32_t, IsHot, const uint32_t *> flags(counts, IsHot{threshold});
-    size_t tmp_bytes = 0;
-    HOT_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, flags, rank, (int)n_cols, stream));
-    HOT_TRY(cudaMalloc(&scan_tmp, tmp_bytes ? tmp_bytes : 16));
-    HOT_TRY(cub::DeviceScan::ExclusiveSum(scan_tmp, tmp_bytes, flags, rank, (int)n_cols, stream));
+    HOT_TRY(cudaMalloc(&rank_t, (size_t)n_cols * 4));
+    HOT_TRY(cudaMalloc(&rank_w, (size_t)n_cols * 4));
+    {
+        using Flags = cub::TransformInputIterator<uint32_t, InBand, const uint32_t *>;
+        Flags in_table(counts, InBand{table_threshold, 0u});
+        Flags in_rest(counts, InBand{threshold, table_threshold});
+        size_t tmp_bytes = 0;
+        HOT_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in_table, rank_t, (int)n_cols, stream));
+        HOT_TRY(cudaMalloc(&scan_tmp, tmp_bytes ? tmp_bytes : 16));
+        HOT_TRY(cub::DeviceScan::ExclusiveSum(scan_tmp, tmp_bytes, in_table, rank_t, (int)n_cols, stream));
+        HOT_TRY(cub::DeviceScan::ExclusiveSum(scan_tmp, tmp_bytes, in_rest, rank_w, (int)n_cols, stream));
+    }
     int32_t *hot_cols = nullptr, *Aj2 = nullptr;
     HOT_TRY(cudaMalloc(&hot_cols, (size_t)K * 4));
     e.plan.hot_cols = hot_cols;
     HOT_TRY(cudaMalloc(&Aj2, (size_t)(nnz > 0 ? nnz : 1) * 4));
     e.plan.Aj2 = Aj2;
-    {
-        const int64_t words = ((int64_t)n_cols + 31) / 32;
-        uint32_t *bitmap = nullptr, *rank32 = nullptr;
-        HOT_TRY(cudaMalloc(&bitmap, (size_t)words * 4));
-        e.plan.bitmap = bitmap;
-        HOT_TRY(cudaMalloc(&rank32, (size_t)words * 4));
-        e.plan.rank32 = rank32;
-        hot_bitmap_kernel<<<grid, 256, 0, stream>>>(counts, rank, n_cols, threshold, bitmap, rank32);
-    }
-    hot_remap_table_kernel<<<grid, 256, 0, stream>>>(counts, n_cols, threshold, rank, hot_cols);
-    hot_remap_kernel<<<grid, 256, 0, stream>>>(Aj, nnz, rank, Aj2);
-    count_launch(4);
+    hot_remap_table_kernel<<<grid, 256, 0, stream>>>(counts, n_cols, threshold, table_threshold, (uint32_t)K_table,
+                                                     rank_t, rank_w, hot_cols);
+    hot_remap_kernel<<<grid, 256, 0, stream>>>(Aj, nnz, rank_t, Aj2);
+    count_launch(5);
     HOT_TRY(cudaGetLastError());
     HOT_TRY(cudaEventRecord(t1, stream));
     HOT_TRY(cudaStreamSynchronize(stream));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, t0, t1);
     e.plan.K = K;
+    e.plan.K_table = K_table;
     e.plan.n_cols = n_cols;
     e.plan.threshold = threshold;
     e.plan.hot_share = (double)mass / (double)(nnz > 0 ? nnz : 1);
+    e.plan.table_share = (double)table_mass / (double)(nnz > 0 ? nnz : 1);
     e.plan.build_ms = ms;
     cleanup();
 #undef HOT_TRY
@@ -263,7 +284,7 @@ void hot_plan_clear() {
 
 // The plan for (Aj, nnz, n_cols) on the current device: found, or built when `may_build`.
 // *out = nullptr when there is none (not built yet, or the matrix has no hot set worth having).
-int hot_plan_get(const int32_t *Aj, int64_t nnz, int32_t n_cols, size_t val_bytes, cudaStream_t stream,
+int hot_plan_get(const int32_t *Aj, int64_t nnz, int32_t n_cols, int64_t k_max, int64_t k_table, cudaStream_t stream,
                  bool may_build, const HotPlan **out) {
     *out = nullptr;
     int dev = -1;
@@ -271,15 +292,16 @@ int hot_plan_get(const int32_t *Aj, int64_t nnz, int32_t n_cols, size_t val_byte
     std::lock_guard<std::mutex> lk(g_plan_mu);
     const PlanKey key{dev, (const void *)Aj};
     auto it = g_plans.find(key);
-    if (it != g_plans.end() && (it->second.nnz != nnz || it->second.n_cols != n_cols)) {
-        entry_free(it->second);  // the address now holds another matrix
+    if (it != g_plans.end() && (it->second.nnz != nnz || it->second.n_cols != n_cols ||
+                                (may_build && (it->second.k_max != k_max || it->second.k_table != k_table)))) {
+        entry_free(it->second);  // the address now holds another matrix, or the sizes asked for changed
         g_plans.erase(it);
         it = g_plans.end();
     }
     if (it == g_plans.end()) {
         if (!may_build) return SPMVB200_OK;
         PlanEntry e;
-        SPMV_TRY(build(Aj, nnz, n_cols, val_bytes, stream, e));
+        SPMV_TRY(build(Aj, nnz, n_cols, k_max, k_table, stream, e));
         it = g_plans.emplace(key, e).first;
     }
     if (!it->second.none) *out = &it->second.plan;

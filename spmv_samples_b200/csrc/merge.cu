@@ -316,26 +316,50 @@ template <> struct __align__(16) WarpTotal<double> { double val; int rid; int pa
 // HOT: Aj is the remapped copy of a hot-x plan (hotx.cu): an index with the top bit set is a rank
 // into the dense copy of the hot columns' x; x_hot_biased = x_hot - 2^31 elements, so that either
 // base + (uint32) index is the address.
-template <int BLOCK, int HAS_PEERS, bool HOT, typename OffT, typename ValT>
+// The shared memory of one tile in flight.
+template <int BLOCK, typename ValT>
+struct __align__(16) TileSmem {
+    ValT scan[BLOCK * kMergeIPT];
+    // row-start flags, one byte per slot.  (One BIT per slot, set with atomicOr, saves 1.8 KB per
+    // 256-thread CTA and fits one more CTA per SM inside the 64 KB carveout, but measured slower:
+    // R-MAT scale 24 1146 -> 1166 us, scale 27 14.70 -> 14.93 ms.)
+    unsigned char flag[BLOCK * kMergeIPT];
+    WarpTotal<ValT> w[BLOCK / 32];
+};
+
+// GROUPS == 1: the CTA is one tile (tile = blockIdx.x, static shared memory, __syncthreads).
+// GROUPS > 1 (merge_tile_table_kernel): the CTA is GROUPS independent groups of BLOCK threads, each
+// working on its own tile out of its own TileSmem with its own named barrier, and `table` holds
+// the x values of ranks 0 .. table_n-1 of the hot-x plan in shared memory.
+template <int BLOCK, int HAS_PEERS, bool HOT, int GROUPS, typename OffT, typename ValT>
 __device__ __forceinline__ void
 merge_tile_reg_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
                     const int32_t *__restrict__ Aj, const ValT *__restrict__ Ax,
                     const ValT *__restrict__ x, ValT *__restrict__ y,
                     const ValT *__restrict__ alpha_dev, const PeerOut &peers,
                     const int32_t *__restrict__ coords_x, int32_t *__restrict__ carry_row,
-                    ValT *__restrict__ carry_val, const ValT *__restrict__ x_hot_biased) {
+                    ValT *__restrict__ carry_val, const ValT *__restrict__ x_hot_biased,
+                    int64_t tile_of_group = 0, TileSmem<BLOCK, ValT> *group_smem = nullptr,
+                    const ValT *table = nullptr, uint32_t table_n = 0) {
     constexpr int IPT = kMergeIPT;
     constexpr int SLOTS = BLOCK * IPT;
     constexpr int TILE = SLOTS - 4;  // path items per tile
-    __shared__ __align__(16) ValT s_scan[SLOTS];
-    // row-start flags, one byte per slot.  (One BIT per slot, set with atomicOr, saves 1.8 KB per
-    // 256-thread CTA and fits one more CTA per SM inside the 64 KB carveout, but measured slower:
-    // R-MAT scale 24 1146 -> 1166 us, scale 27 14.70 -> 14.93 ms.)
-    __shared__ __align__(16) unsigned char s_flag[SLOTS];
-    __shared__ WarpTotal<ValT> s_w[BLOCK / 32];
+    TileSmem<BLOCK, ValT> *sm = group_smem;
+    if constexpr (GROUPS == 1) {
+        __shared__ TileSmem<BLOCK, ValT> s_cta;
+        sm = &s_cta;
+    }
+    ValT *const s_scan = sm->scan;
+    unsigned char *const s_flag = sm->flag;
+    WarpTotal<ValT> *const s_w = sm->w;
+    const int grp = GROUPS == 1 ? 0 : (int)(threadIdx.x / BLOCK);
+    auto tile_sync = [grp]() {
+        if (GROUPS == 1) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(BLOCK) : "memory");
+    };
 
-    const int tid = threadIdx.x;
-    const int64_t tile = blockIdx.x;
+    const int tid = GROUPS == 1 ? (int)threadIdx.x : (int)(threadIdx.x % BLOCK);
+    const int64_t tile = GROUPS == 1 ? (int64_t)blockIdx.x : tile_of_group;
     const int64_t total = (int64_t)n_rows + (int64_t)nnz;
     const int64_t d0 = tile * TILE;
     const int64_t d1 = d0 + TILE < total ? d0 + TILE : total;
@@ -379,7 +403,7 @@ merge_tile_reg_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
         }
     }
     const ValT alpha = alpha_dev ? __ldg(alpha_dev) : (ValT)1;
-    __syncthreads();  // flags are clear
+    tile_sync();  // flags are clear
 
     // ---- row-start flags, one thread per row end (Ap read coalesced, no staging)
     for (int j = tid; j < R; j += BLOCK) {
@@ -393,7 +417,14 @@ merge_tile_reg_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
         for (int k = 0; k < IPT; ++k) {
             const int i = slot0 + k - shift;
             const ValT *src = HOT ? (c[k] < 0 ? x_hot_biased : x) + (uint32_t)c[k] : x + c[k];
-            xv[k] = (i >= 0 && i < Z) ? ldg_hint(src, pol_x) : (ValT)0;
+            if (GROUPS > 1) {
+                // rank of a hot column, >= 2^31 for any other: one compare picks the table
+                const uint32_t r = (uint32_t)c[k] ^ 0x80000000u;
+                if (i >= 0 && i < Z) xv[k] = r < table_n ? table[r] : ldg_hint(src, pol_x);
+                else xv[k] = (ValT)0;
+            } else {
+                xv[k] = (i >= 0 && i < Z) ? ldg_hint(src, pol_x) : (ValT)0;
+            }
         }
 #pragma unroll
         for (int k = 0; k < IPT; ++k) {
@@ -401,7 +432,7 @@ merge_tile_reg_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
             p[k] = (i >= 0 && i < Z) ? p[k] * xv[k] : (ValT)0;
         }
     }
-    __syncthreads();  // flags are set
+    tile_sync();  // flags are set
 
     // ---- segmented scan (as in the TMA variant)
     const uint2 fw = *reinterpret_cast<const uint2 *>(s_flag + slot0);
@@ -426,7 +457,7 @@ merge_tile_reg_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
     ValT ev = __shfl_up_sync(0xffffffffu, val, 1);
     if (lane == 0) ev = (ValT)0;
     const bool ef = (fmask & ((1u << lane) - 1u)) != 0u;
-    __syncthreads();
+    tile_sync();
     ValT wv = (ValT)0;
 #pragma unroll
     for (int w = 0; w < BLOCK / 32; ++w) {
@@ -442,7 +473,7 @@ merge_tile_reg_body(int32_t n_rows, OffT nnz, const OffT *__restrict__ Ap,
         p[k] = run;
     }
     sts8(s_scan + slot0, p);
-    __syncthreads();
+    tile_sync();
 
     // ---- one thread per row end: the row's total is the scan value at its last nonzero.
     // Row sx+j covers tile-local nonzeros [max(Ap[sx+j]-sy, 0), Ap[sx+j+1]-sy).
@@ -683,7 +714,7 @@ __device__ __forceinline__ void merge_tile_dispatch(MERGE_REG_KERNEL_ARGS, const
         merge_tile_mark_body<BLOCK, HAS_PEERS, HOT, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers,
                                                                 coords_x, carry_row, carry_val, x_hot_biased);
     else
-        merge_tile_reg_body<BLOCK, HAS_PEERS, HOT, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers,
+        merge_tile_reg_body<BLOCK, HAS_PEERS, HOT, 1, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers,
                                                                coords_x, carry_row, carry_val, x_hot_biased);
 }
 template <int ALGO, int BLOCK, int HAS_PEERS, typename OffT, typename ValT>
@@ -708,6 +739,52 @@ __global__ void __launch_bounds__(BLOCK)
 merge_tile_hot_kernel(MERGE_REG_KERNEL_ARGS, const ValT *__restrict__ x_hot_biased) {
     merge_tile_dispatch<ALGO, BLOCK, HAS_PEERS, true, OffT, ValT>(n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers,
                                                                   coords_x, carry_row, carry_val, x_hot_biased);
+}
+// The persistent form of the hot-x tile kernel: one CTA per SM, kTableGroups groups of 128 threads
+// that each walk over tiles (tile = round * gridDim.x * groups + blockIdx.x * groups + group: at
+// any moment the SMs work on neighbouring tiles, as a plain launch would), so that shared memory
+// can hold a TABLE: the x values of the plan's first table_n ranks, its most frequent columns.
+// Why: ncu puts the flag-form kernel on R-MAT scale 24 at 86 % of l1tex__m_l1tex2xbar_req_cycles --
+// one request per cycle per SM from the L1 to the L2 is the wall every CSR kernel here runs into
+// (~270 G gathers/s on the chip, tools/l2_gather_probe.cu), and only 7 % of the gathers hit the
+// L1.  A gather served from shared memory never becomes such a request.  On R-MAT the 13 K most
+// frequent columns of scale 24 take 28 % of the gathers, the 3.3 K of scale 27 8 %.
+// Measured (tools/table_sweep.py, L2 flushed, y bit-identical in every row):
+//   scale 24 (x 64 MB, table-only plan): 1095 us plain -> 1105 persistent without a table -> 1045
+//     with the 13 K table; request cycles 86 -> 73 %, the kernel is then short of warps (8 per
+//     scheduler at 56 registers; two or three smaller CTAs per SM, each with its own table, were
+//     slower: 1070 / 1175 / 1367 us);
+//   scale 27 (hot-x plan + table): 11.27 ms -> 10.89 persistent -> 10.34 with the 3.3 K table.
+// The table takes its space from the L1, which is what holds the gathers in flight: 99 KB of
+// shared memory (tiles + 58 KB of table) is the best size on both; at scale 24 a 154 KB table with
+// 40 % of the gathers is slower than none (1117 us), at scale 27 the 83 KB table with 19 % gives
+// 10.99 ms.  Hence option "hot_x_table_bytes".  The tile body is the flag form's, with group-local
+// barriers; products and their order are unchanged.
+#ifndef SPMV_TABLE_GROUPS
+#define SPMV_TABLE_GROUPS 8
+#endif
+constexpr int kTableGroups = SPMV_TABLE_GROUPS;
+#ifndef SPMV_TABLE_CTAS
+#define SPMV_TABLE_CTAS 1
+#endif
+constexpr int kTableCtas = SPMV_TABLE_CTAS;   // CTAs per SM, each with its own copy of the table
+constexpr int kTableBlock = 128;
+template <int HAS_PEERS, typename OffT, typename ValT>
+__global__ void __launch_bounds__(kTableGroups *kTableBlock, kTableCtas)
+merge_tile_table_kernel(MERGE_REG_KERNEL_ARGS, const ValT *__restrict__ x_hot_biased,
+                        const ValT *__restrict__ x_hot, uint32_t table_n, int64_t num_tiles) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using Smem = TileSmem<kTableBlock, ValT>;
+    Smem *const groups = reinterpret_cast<Smem *>(smem_raw);
+    ValT *const table = reinterpret_cast<ValT *>(smem_raw + sizeof(Smem) * kTableGroups);
+    for (uint32_t i = threadIdx.x; i < table_n; i += kTableGroups * kTableBlock) table[i] = __ldg(x_hot + i);
+    __syncthreads();
+    const int grp = (int)(threadIdx.x / kTableBlock);
+    for (int64_t tile = (int64_t)blockIdx.x * kTableGroups + grp; tile < num_tiles;
+         tile += (int64_t)gridDim.x * kTableGroups)
+        merge_tile_reg_body<kTableBlock, HAS_PEERS, true, kTableGroups, OffT, ValT>(
+            n_rows, nnz, Ap, Aj, Ax, x, y, alpha_dev, peers, coords_x, carry_row, carry_val, x_hot_biased, tile,
+            groups + grp, table, table_n);
 }
 #undef MERGE_REG_KERNEL_ARGS
 
@@ -1094,11 +1171,26 @@ int launch_merge(const SpmvProblem<OffT, ValT> &p) {
         const bool mc_f32 = p.peers.n < 0 && sizeof(ValT) == 4 && flags_form;
         // hot-x plan (hotx.cu): by default only for a caller that vouches for an unchanged matrix
         // and an x far longer than the TLB and the L2 reach
+        // Two uses of it.  (a) x far longer than the TLB and the L2 reach ("hot_x_min_bytes"): up to
+        // "hot_x_max_bytes" of the most frequent columns' x in one dense array.  (b) whatever the
+        // size of x: the few thousand most frequent columns in a shared-memory table of the
+        // persistent tile kernel (merge_tile_table_kernel; "hot_x_table" -1 = fp32 only, 0 = off,
+        // 1 = on; "hot_x_table_bytes" = the kernel's dynamic shared memory, tiles and table).
         const int64_t hot_opt = option_get("hot_x", -1);
-        const bool want_hot = hot_opt > 0 || (hot_opt < 0 && p.reuse_partition &&
-                              (int64_t)p.n_cols * (int64_t)sizeof(ValT) > option_get("hot_x_min_bytes", 256ll << 20));
+        const int64_t tbl_opt = option_get("hot_x_table", -1);
+        const bool tbl_ok = RB == kTableBlock && (tbl_opt > 0 || (tbl_opt < 0 && sizeof(ValT) == 4 && flags_form));
+        constexpr int64_t tile_smem = (int64_t)sizeof(TileSmem<kTableBlock, ValT>) * kTableGroups;
+        // the option is per SM; every CTA has 1 KB reserved by the system inside a carveout size
+        int64_t tbl_bytes = option_get("hot_x_table_bytes", 99 << 10);
+        if (tbl_bytes > 226 << 10) tbl_bytes = 226 << 10;
+        tbl_bytes = (tbl_bytes + 1024) / kTableCtas - 1024;
+        const int64_t k_table = tbl_ok && tbl_bytes > tile_smem ? (tbl_bytes - tile_smem) / (int64_t)sizeof(ValT) : 0;
+        const bool big_x = (int64_t)p.n_cols * (int64_t)sizeof(ValT) > option_get("hot_x_min_bytes", 256ll << 20);
+        const bool want_hot = hot_opt > 0 || (hot_opt < 0 && p.reuse_partition && (big_x || k_table > 0));
+        const int64_t k_max = (hot_opt > 0 || big_x) ? option_get("hot_x_max_bytes", 32 << 20) / (int64_t)sizeof(ValT)
+                                                     : k_table;
         const HotPlan *hot = nullptr;
-        if (want_hot) SPMV_TRY(hot_plan_get(p.Aj, (int64_t)p.nnz, p.n_cols, sizeof(ValT), p.stream, true, &hot));
+        if (want_hot) SPMV_TRY(hot_plan_get(p.Aj, (int64_t)p.nnz, p.n_cols, k_max, k_table, p.stream, true, &hot));
         // a call without the flag says "this may be a new matrix": a plan left at this address by
         // an earlier one must not survive it
         else if (hot_opt < 0 && !p.reuse_partition) hot_plan_drop(p.Aj);
@@ -1107,6 +1199,29 @@ int launch_merge(const SpmvProblem<OffT, ValT> &p) {
         if (hot) {
             const ValT *x_hot = nullptr;
             SPMV_TRY(hot_gather<ValT>(*hot, p.x, p.stream, &x_hot));
+            const ValT *x_hot_biased = x_hot - ((ptrdiff_t)1 << 31);
+            if (k_table > 0 && hot->K_table > 0) {
+                auto tkernel = p.peers.n < 0 ? merge_tile_table_kernel<2, OffT, ValT>
+                               : has_peers   ? merge_tile_table_kernel<1, OffT, ValT>
+                                             : merge_tile_table_kernel<0, OffT, ValT>;
+                int64_t tn = hot->K_table < k_table ? hot->K_table : k_table;
+                const int64_t cap = option_get("hot_x_table_limit", -1);   // experiments: fewer entries than planned
+                if (cap >= 0 && cap < tn) tn = cap;
+                const uint32_t table_n = (uint32_t)tn;
+                const size_t smem = (size_t)tile_smem + (size_t)table_n * sizeof(ValT);
+                SPMV_TRY(apply_max_dynamic_smem(reinterpret_cast<const void *>(tkernel), (int64_t)smem));
+                const DeviceInfo *di = nullptr;
+                SPMV_TRY(current_device_info(&di));
+                const int64_t want_ctas = (num_tiles + kTableGroups - 1) / kTableGroups;
+                const int64_t max_ctas = (int64_t)di->sm_count * kTableCtas;
+                make_launch_cfg(lc, dim3((unsigned)(want_ctas < max_ctas ? want_ctas : max_ctas)),
+                                dim3(kTableGroups * kTableBlock), smem, p.stream, p.x, (size_t)p.n_cols * sizeof(ValT));
+                KernelTimerScope timed(p.stream);
+                SPMV_CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, tkernel, p.n_rows, p.nnz, p.Ap, hot->Aj2, p.Ax, p.x, p.y,
+                                                 p.alpha_dev, p.peers, (const int32_t *)coords,
+                                                 static_cast<int32_t *>(crow), static_cast<ValT *>(cval),
+                                                 x_hot_biased, x_hot, table_n, num_tiles));
+            } else {
             auto kernel = flags_form ? (mc_f32    ? merge_tile_hot_kernel<1, RB, 2, OffT, ValT>
                                         : has_peers ? merge_tile_hot_kernel<1, RB, 1, OffT, ValT>
                                                   : merge_tile_hot_kernel<1, RB, 0, OffT, ValT>)
@@ -1114,12 +1229,12 @@ int launch_merge(const SpmvProblem<OffT, ValT> &p) {
                                         : occ     ? merge_tile_hot_kernel_occ8<0, RB, 0, OffT, ValT>
                                                   : merge_tile_hot_kernel<0, RB, 0, OffT, ValT>);
             SPMV_TRY(apply_carveout(reinterpret_cast<const void *>(kernel), carveout));
-            const ValT *x_hot_biased = x_hot - ((ptrdiff_t)1 << 31);
             KernelTimerScope timed(p.stream);
             SPMV_CUDA_TRY(cudaLaunchKernelEx(&lc.cfg, kernel, p.n_rows, p.nnz, p.Ap, hot->Aj2, p.Ax, p.x, p.y,
                                              p.alpha_dev, p.peers, (const int32_t *)coords,
                                              static_cast<int32_t *>(crow), static_cast<ValT *>(cval),
                                              x_hot_biased));
+            }
         } else {
             auto kernel = flags_form ? (mc_f32    ? merge_tile_reg_kernel<1, RB, 2, OffT, ValT>
                                         : has_peers ? merge_tile_reg_kernel<1, RB, 1, OffT, ValT>   // 40 regs, no spill

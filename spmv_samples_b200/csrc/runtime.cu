@@ -58,6 +58,10 @@ std::map<std::string, int64_t> &options() {
                                  // passes SPMVB200_FLAG_STATIC_PATTERN and x is longer than
                                  // "hot_x_min_bytes"; 0 = never; 1 = always (plan keyed on the Aj pointer)
         {"hot_x_min_bytes", 256ll << 20},
+        {"hot_x_table", -1},     // shared-memory table of the most frequent columns (persistent merge tile kernel):
+                                 // -1 = fp32 flag form, 0 = never, 1 = always
+        {"hot_x_table_limit", -1},  // experiments: use at most this many table entries (0: persistent kernel, no table)
+        {"hot_x_table_bytes", 99 << 10},  // dynamic shared memory of that kernel (8 tiles in flight + table)
         {"assume_static_pattern", 0},  // 1: every call is treated as carrying SPMVB200_FLAG_STATIC_PATTERN
         {"side_stream", 0},      // 1: small kernels a big one depends on (partition, x_hot refill) run on a side
                                  // stream forked / joined with events (measured: no gain outside the profiler)
@@ -273,6 +277,19 @@ int apply_carveout(const void *kernel, int64_t percent) {
     SPMV_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                        percent < 0 ? (int)cudaSharedmemCarveoutDefault : (int)percent));
     applied[key] = percent;
+    return SPMVB200_OK;
+}
+
+int apply_max_dynamic_smem(const void *kernel, int64_t bytes) {
+    const DeviceInfo *di = nullptr;
+    SPMV_TRY(current_device_info(&di));
+    static std::map<std::pair<int, const void *>, int64_t> applied;
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto key = std::make_pair(di->device, kernel);
+    auto it = applied.find(key);
+    if (it != applied.end() && it->second >= bytes) return SPMVB200_OK;
+    SPMV_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    applied[key] = bytes;
     return SPMVB200_OK;
 }
 

@@ -302,8 +302,12 @@ def hot_x_info(Aj) -> dict:
     k, share, ms = C.c_int64(0), C.c_double(0.0), C.c_double(0.0)
     with torch.cuda.device(Aj.device):
         st = _lib.lib().spmvb200_hot_x_info(_ptr(Aj), C.byref(k), C.byref(share), C.byref(ms))
-    _lib.check(st, "spmvb200_hot_x_info")
-    return {"hot_columns": int(k.value), "hot_share": float(share.value), "build_ms": float(ms.value)}
+        _lib.check(st, "spmvb200_hot_x_info")
+        tk, tshare = C.c_int64(0), C.c_double(0.0)
+        st = _lib.lib().spmvb200_hot_x_table_info(_ptr(Aj), C.byref(tk), C.byref(tshare))
+    _lib.check(st, "spmvb200_hot_x_table_info")
+    return {"hot_columns": int(k.value), "hot_share": float(share.value), "build_ms": float(ms.value),
+            "table_columns": int(tk.value), "table_share": float(tshare.value)}
 
 
 def release_cache() -> None:

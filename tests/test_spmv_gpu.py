@@ -647,12 +647,14 @@ def test_reference_labels_are_aliases():
 
 
 # ------------------------------------------------------------------ hot-x plan (csrc/hotx.cu)
-@pytest.mark.parametrize("fill", [0, 1, 2])
+@pytest.mark.parametrize("table", [0, 1])
+@pytest.mark.parametrize("fill", [0, 1])
 @pytest.mark.parametrize("off", [np.int32, np.int64])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-def test_hot_x_plan_is_bit_identical(dtype, off, fill):
-    """The remapped Aj + dense x_hot change where x is read from, not what is added or in which
-    order: y must be bit-identical to the plain merge kernel's, and within tolerance of the oracle."""
+def test_hot_x_plan_is_bit_identical(dtype, off, fill, table):
+    """The remapped Aj + dense x_hot (+ the shared-memory table of the persistent tile kernel) change
+    where x is read from, not what is added or in which order: y must be bit-identical to the plain
+    merge kernel's, and within tolerance of the oracle."""
     from spmv_samples_b200 import spmv
     Ap, Aj, Ax = g.rmat(15, 16, 21, dtype=dtype, offset_dtype=off)
     x = g.gen_x(5, 1 << 15, dtype)
@@ -660,10 +662,17 @@ def test_hot_x_plan_is_bit_identical(dtype, off, fill):
     y0 = torch.full((1 << 15,), float("nan"), dtype=dAx.dtype, device="cuda")
     y1 = torch.full_like(y0, float("nan"))
     spmv.release_cache()
+    spmv.set_option("hot_x", 0)
+    if table:   # the table kernel has the flag-form tile body: compare like with like (fp64 defaults to markers)
+        spmv.set_option("merge_algo", 1)
     spmv.SpMV("merge", 1 << 15, 1 << 15, Aj.size, dAp, dAj, dAx, dx, y0)
     spmv.set_option("hot_x", 1)
     spmv.set_option("hot_x_max_bytes", 4096 * x.itemsize)     # 4096 hot columns
-    spmv.set_option("hot_x_fill", fill)                       # x_hot by gather (1) / by a sweep over x (2)
+    spmv.set_option("hot_x_fill", fill)
+    spmv.set_option("hot_x_table", table)
+    # 8 tiles in flight (scan values, flags, warp totals) + a table of 1000 values: ranks below
+    # 1000 come from shared memory, the other hot columns from x_hot, the rest from x
+    spmv.set_option("hot_x_table_bytes", 8 * (1024 * x.itemsize + 1024 + 4 * 2 * x.itemsize) + 1000 * x.itemsize)
     try:
         spmv.SpMV("merge", 1 << 15, 1 << 15, Aj.size, dAp, dAj, dAx, dx, y1)
         torch.cuda.synchronize()
@@ -677,15 +686,52 @@ def test_hot_x_plan_is_bit_identical(dtype, off, fill):
         spmv.set_option("hot_x", -1)
         spmv.set_option("hot_x_max_bytes", 32 << 20)
         spmv.set_option("hot_x_fill", 0)
+        spmv.set_option("hot_x_table", -1)
+        spmv.set_option("hot_x_table_bytes", 99 << 10)
+        spmv.set_option("merge_algo", -1)
         spmv.release_cache()
     assert 0 < info["hot_columns"] <= 4096 and 0.25 <= info["hot_share"] <= 1.0
+    assert (0 < info["table_columns"] <= 1000 and 0 < info["table_share"] < info["hot_share"]) if table \
+        else info["table_columns"] == 0
     assert np.array_equal(y0.cpu().numpy(), y1.cpu().numpy())
     assert_within_tolerance(y1.cpu().numpy(), Ap, Aj, Ax, x, "merge + hot_x")
     assert_within_tolerance(y2.cpu().numpy(), Ap, Aj, Ax, x2, "merge + hot_x, second x")
-    # the hot set is the set of most frequent columns
+    # the hot set is the set of most frequent columns, and so is the table class within it
     cnt = np.bincount(Aj, minlength=1 << 15)
-    thr = np.sort(cnt)[::-1][info["hot_columns"] - 1]
+    by_count = np.sort(cnt)[::-1]
+    thr = by_count[info["hot_columns"] - 1]
     assert abs(info["hot_share"] - cnt[cnt >= thr].sum() / Aj.size) < 1e-12
+    if table:
+        thr = by_count[info["table_columns"] - 1]
+        assert abs(info["table_share"] - cnt[cnt >= thr].sum() / Aj.size) < 1e-12
+
+
+def test_table_plan_for_a_short_x_under_the_static_pattern_flag():
+    """Default options, x far below "hot_x_min_bytes": a caller that vouches for the pattern gets the
+    table-only plan (every hot column is a table column) from its first flagged call on, an
+    unflagged call drops it again; y stays bit-identical throughout."""
+    from spmv_samples_b200 import spmv
+    Ap, Aj, Ax = g.rmat(16, 16, 33)
+    n = 1 << 16
+    x = g.gen_x(9, n)
+    dAp, dAj, dAx, dx = dev(Ap), dev(Aj), dev(Ax), dev(x)
+    ys = []
+    spmv.release_cache()
+    try:
+        for flagged in (False, True, True, False):
+            y = torch.full((n,), float("nan"), device="cuda")
+            spmv.spmv_ex("merge", dAp, dAj, dAx, dx, y, n_cols=n, static_pattern=flagged)
+            torch.cuda.synchronize()
+            info = spmv.hot_x_info(dAj)
+            if flagged:
+                assert info["table_columns"] == info["hot_columns"] > 0 and info["table_share"] >= 0.10
+            else:
+                assert info["hot_columns"] == 0
+            ys.append(y.cpu().numpy())
+    finally:
+        spmv.release_cache()
+    assert all(np.array_equal(ys[0], v) for v in ys[1:])
+    assert_within_tolerance(ys[1], Ap, Aj, Ax, x, "merge + table plan")
 
 
 def test_hot_x_plan_declines_a_flat_column_distribution():
