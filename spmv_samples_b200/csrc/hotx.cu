@@ -90,26 +90,53 @@ hot_hist_kernel(const uint32_t *__restrict__ counts, int64_t n_cols, unsigned lo
     }
 }
 
-// two classes of hot columns: count >= hi ("table": the few thousand most frequent ones, which the
-// persistent tile kernel keeps in shared memory) and lo <= count < hi
+// Classes of columns: 1 = table (the most frequent ones, which the persistent tile kernel keeps in
+// shared memory), 2 = the other hot columns, 0 = not hot.  The table class is every column seen
+// at least `table_threshold` times plus, to fill the table to its capacity, the first `part_take`
+// columns (in column order) of the next lower count bucket [part_lo, table_threshold); the rest of
+// that bucket is class `part_rest`.
 struct InBand {
-    uint32_t lo, hi;   // lo <= n < hi; hi == 0 means no upper bound
+    uint32_t lo, hi;   // lo <= n < hi
     __host__ __device__ __forceinline__ uint32_t operator()(const uint32_t &n) const {
-        return (n >= lo && (hi == 0u || n < hi)) ? 1u : 0u;
+        return (n >= lo && n < hi) ? 1u : 0u;
     }
 };
+struct IsClass {
+    unsigned char which;
+    __host__ __device__ __forceinline__ uint32_t operator()(const unsigned char &c) const { return c == which ? 1u : 0u; }
+};
 
-// Ranks: the table class first (0 .. K_table-1), the other hot columns after it, both in column
-// order.  rank_t / rank_w hold the exclusive scans of the two class flags on entry; rank_t is the
-// remap table on exit (hot column -> 0x80000000 | rank, any other -> itself).
+// part_rank: exclusive scan of InBand{part_lo, table_threshold} over the counts
 __global__ void __launch_bounds__(256)
-hot_remap_table_kernel(const uint32_t *__restrict__ counts, int64_t n_cols, uint32_t threshold, uint32_t table_threshold,
-                       uint32_t K_table, uint32_t *__restrict__ rank_t, const uint32_t *__restrict__ rank_w,
-                       int32_t *__restrict__ hot_cols) {
+hot_class_kernel(const uint32_t *__restrict__ counts, int64_t n_cols, uint32_t threshold, uint32_t table_threshold,
+                 uint32_t part_lo, uint32_t part_take, unsigned char part_rest, const uint32_t *__restrict__ part_rank,
+                 unsigned char *__restrict__ cls, unsigned long long *__restrict__ table_mass) {
+    unsigned long long mass = 0;
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cols; c += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t n = counts[c];
-        if (n >= threshold) {
-            const uint32_t r = n >= table_threshold ? rank_t[c] : K_table + rank_w[c];
+        unsigned char k = 0;
+        if (n >= table_threshold) k = 1;
+        else if (part_take > 0u && n >= part_lo) k = part_rank[c] < part_take ? 1 : part_rest;
+        else if (n >= threshold) k = 2;
+        cls[c] = k;
+        if (k == 1) mass += n;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mass += __shfl_down_sync(0xffffffffu, mass, d);
+    if ((threadIdx.x & 31) == 0 && mass) atomicAdd(table_mass, mass);
+}
+
+// rank_t / rank_w hold the exclusive scans of the two class flags on entry; rank_t is the remap
+// table on exit (hot column -> 0x80000000 | rank, any other -> itself).  Ranks: the table class
+// first (0 .. K_table-1), the other hot columns after it, both in column order.
+__global__ void __launch_bounds__(256)
+hot_remap_table_kernel(const unsigned char *__restrict__ cls, int64_t n_cols, uint32_t K_table,
+                       uint32_t *__restrict__ rank_t, const uint32_t *__restrict__ rank_w,
+                       int32_t *__restrict__ hot_cols) {
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cols; c += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned char k = cls[c];
+        if (k) {
+            const uint32_t r = k == 1 ? rank_t[c] : K_table + rank_w[c];
             hot_cols[r] = (int32_t)c;
             rank_t[c] = 0x80000000u | r;
         } else {
@@ -167,12 +194,14 @@ int build(const int32_t *Aj, int64_t nnz, int32_t n_cols, int64_t k_max, int64_t
     SPMV_CUDA_TRY(cudaEventRecord(t0, stream));
 
     uint32_t *counts = nullptr, *rank_t = nullptr, *rank_w = nullptr;
+    unsigned char *cls = nullptr;
     unsigned long long *hist = nullptr;
     void *scan_tmp = nullptr;
     auto cleanup = [&]() {
         if (counts) cudaFree(counts);
         if (rank_t) cudaFree(rank_t);
         if (rank_w) cudaFree(rank_w);
+        if (cls) cudaFree(cls);
         if (hist) cudaFree(hist);
         if (scan_tmp) cudaFree(scan_tmp);
         if (t0) cudaEventDestroy(t0);
@@ -201,25 +230,45 @@ int build(const int32_t *Aj, int64_t nnz, int32_t n_cols, int64_t k_max, int64_t
     HOT_TRY(cudaStreamSynchronize(stream));
 
     // thresholds: as many of the most frequent columns as fit x_hot (a column seen once gains
-    // nothing), and among them as many as fit the shared-memory table
-    uint32_t threshold = 0, table_threshold = 0;
-    int64_t K = 0, K_table = 0;
-    unsigned long long mass = 0, table_mass = 0;
+    // nothing), and among them as many as fit the shared-memory table: whole count buckets, then
+    // part of the next one
+    uint32_t threshold = 0, table_threshold = 0xffffffffu, part_lo = 0;
+    int64_t K = 0, K_table = 0, part_take = 0;
+    unsigned long long mass = 0;
+    bool part_rest_hot = true;   // the columns of the split bucket that do not fit the table: still hot?
     {
         int64_t cols = 0;
         unsigned long long m = 0;
+        bool table_open = k_table > 0;
         for (int b = kCountBuckets - 1; b >= count_bucket(2u); --b) {
-            if (cols + (int64_t)h[b] > k_max) break;
+            if (h[b] == 0) continue;
+            if (cols + (int64_t)h[b] > k_max) {
+                // a plan that is all table (k_max == k_table) still fills the table from this bucket;
+                // the rest of the bucket stays cold
+                if (table_open && k_table > K_table && k_max == k_table) {
+                    part_lo = bucket_lower_edge(b);
+                    part_take = k_table - K_table;
+                    part_rest_hot = false;
+                    threshold = part_lo;
+                    K = cols + part_take;
+                    mass = m + (unsigned long long)part_take * part_lo;   // a lower bound; the exact sum comes from the device
+                }
+                break;
+            }
             cols += (int64_t)h[b];
             m += h[kCountBuckets + b];
-            if (h[b] == 0) continue;
             threshold = bucket_lower_edge(b);
             K = cols;
             mass = m;
-            if (cols <= k_table) {
-                table_threshold = threshold;
-                K_table = cols;
-                table_mass = m;
+            if (table_open) {
+                if (cols <= k_table) {
+                    table_threshold = threshold;
+                    K_table = cols;
+                } else {
+                    part_lo = threshold;
+                    part_take = k_table - K_table;
+                    table_open = false;
+                }
             }
         }
     }
@@ -229,34 +278,42 @@ int build(const int32_t *Aj, int64_t nnz, int32_t n_cols, int64_t k_max, int64_t
     e.k_table = k_table;
     // not worth a second copy of Aj unless the hot columns take a good share of the gathers: a
     // quarter for the dense x_hot, a tenth when all of them sit in the shared-memory table
-    if (K == 0 || (double)mass < (K == K_table ? 0.10 : 0.25) * (double)nnz) {
+    if (K == 0 || (double)mass < (K == K_table + part_take ? 0.10 : 0.25) * (double)nnz) {
         cleanup();
         e.none = true;
         return SPMVB200_OK;
     }
-    if (K_table == 0) table_threshold = 0xffffffffu;
 
     HOT_TRY(cudaMalloc(&rank_t, (size_t)n_cols * 4));
     HOT_TRY(cudaMalloc(&rank_w, (size_t)n_cols * 4));
+    HOT_TRY(cudaMalloc(&cls, (size_t)n_cols));
     {
-        using Flags = cub::TransformInputIterator<uint32_t, InBand, const uint32_t *>;
-        Flags in_table(counts, InBand{table_threshold, 0u});
-        Flags in_rest(counts, InBand{threshold, table_threshold});
-        size_t tmp_bytes = 0;
-        HOT_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in_table, rank_t, (int)n_cols, stream));
+        size_t tmp_bytes = 0, tb = 0;
+        cub::TransformInputIterator<uint32_t, InBand, const uint32_t *> in_part(counts, InBand{part_lo, table_threshold});
+        cub::TransformInputIterator<uint32_t, IsClass, const unsigned char *> in_table(cls, IsClass{1});
+        cub::TransformInputIterator<uint32_t, IsClass, const unsigned char *> in_rest(cls, IsClass{2});
+        HOT_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in_part, rank_w, (int)n_cols, stream));
+        HOT_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tb, in_table, rank_t, (int)n_cols, stream));
+        if (tb > tmp_bytes) tmp_bytes = tb;
         HOT_TRY(cudaMalloc(&scan_tmp, tmp_bytes ? tmp_bytes : 16));
+        if (part_take > 0) HOT_TRY(cub::DeviceScan::ExclusiveSum(scan_tmp, tmp_bytes, in_part, rank_w, (int)n_cols, stream));
+        HOT_TRY(cudaMemsetAsync(hist, 0, sizeof(unsigned long long), stream));
+        hot_class_kernel<<<grid, 256, 0, stream>>>(counts, n_cols, threshold, table_threshold, part_lo, (uint32_t)part_take,
+                                                   part_rest_hot ? 2 : 0, rank_w, cls, hist);
         HOT_TRY(cub::DeviceScan::ExclusiveSum(scan_tmp, tmp_bytes, in_table, rank_t, (int)n_cols, stream));
         HOT_TRY(cub::DeviceScan::ExclusiveSum(scan_tmp, tmp_bytes, in_rest, rank_w, (int)n_cols, stream));
     }
+    K_table += part_take;
+    unsigned long long table_mass = 0;
+    HOT_TRY(cudaMemcpyAsync(&table_mass, hist, sizeof(table_mass), cudaMemcpyDeviceToHost, stream));
     int32_t *hot_cols = nullptr, *Aj2 = nullptr;
     HOT_TRY(cudaMalloc(&hot_cols, (size_t)K * 4));
     e.plan.hot_cols = hot_cols;
     HOT_TRY(cudaMalloc(&Aj2, (size_t)(nnz > 0 ? nnz : 1) * 4));
     e.plan.Aj2 = Aj2;
-    hot_remap_table_kernel<<<grid, 256, 0, stream>>>(counts, n_cols, threshold, table_threshold, (uint32_t)K_table,
-                                                     rank_t, rank_w, hot_cols);
+    hot_remap_table_kernel<<<grid, 256, 0, stream>>>(cls, n_cols, (uint32_t)K_table, rank_t, rank_w, hot_cols);
     hot_remap_kernel<<<grid, 256, 0, stream>>>(Aj, nnz, rank_t, Aj2);
-    count_launch(5);
+    count_launch(6);
     HOT_TRY(cudaGetLastError());
     HOT_TRY(cudaEventRecord(t1, stream));
     HOT_TRY(cudaStreamSynchronize(stream));
@@ -266,6 +323,7 @@ int build(const int32_t *Aj, int64_t nnz, int32_t n_cols, int64_t k_max, int64_t
     e.plan.K_table = K_table;
     e.plan.n_cols = n_cols;
     e.plan.threshold = threshold;
+    if (!part_rest_hot) mass = table_mass;   // an all-table plan: the device's exact sum replaces the lower bound
     e.plan.hot_share = (double)mass / (double)(nnz > 0 ? nnz : 1);
     e.plan.table_share = (double)table_mass / (double)(nnz > 0 ? nnz : 1);
     e.plan.build_ms = ms;

@@ -355,8 +355,13 @@ class PowerIteration:
     def shard_local_ms(self, steps: int = 5):
         """Mean duration of this rank's local part of a step -- everything between the step
         barriers that does not wait for a peer: partition, tile kernel, carry fix-up, sum of
-        squares -- over `steps` steps, for every rank (the same list on all ranks).  CUDA events
-        on the stream the step runs on."""
+        squares -- over `steps` steps (after two warm-up steps), for every rank (the same list on
+        all ranks).  CUDA events on the stream the step runs on."""
+        # two untimed steps first: the first SpMV on a new shard searches the partition and the
+        # second builds the hot-x / table plan (tens of ms on a large shard), neither of which a
+        # later step pays
+        for _ in range(2):
+            self.step()
         torch.cuda.synchronize()
         self._local_events = []
         try:

@@ -541,13 +541,25 @@ def test_static_pattern_flag_reuses_and_never_goes_stale():
     y0 = torch.empty(n, device="cuda")
     y1 = torch.empty(n, device="cuda")
     launches = []
-    for flag in (False, True, True):
+    spmv.set_option("hot_x", 0)        # launch counts of the plain kernels: no plan build on the flagged call
+    try:
+        for flag in (False, True, True):
+            before = spmv.launch_count()
+            spmv.spmv_ex("merge", dAp, dAj, dAx, dx, y1 if flag else y0, static_pattern=flag)
+            launches.append(spmv.launch_count() - before)
+        torch.cuda.synchronize()
+    finally:
+        spmv.set_option("hot_x", -1)
+    assert torch.equal(y0, y1)
+    assert launches[1] == launches[0] - 1 and launches[2] == launches[1]     # the search is skipped
+    # default options: the flagged calls build the table plan once (more launches), then refill + tile + fixup
+    for flag in (True, True):
         before = spmv.launch_count()
-        spmv.spmv_ex("merge", dAp, dAj, dAx, dx, y1 if flag else y0, static_pattern=flag)
+        spmv.spmv_ex("merge", dAp, dAj, dAx, dx, y1, static_pattern=flag)
         launches.append(spmv.launch_count() - before)
     torch.cuda.synchronize()
     assert torch.equal(y0, y1)
-    assert launches[1] == launches[0] - 1 and launches[2] == launches[1]     # the search is skipped
+    assert launches[3] > launches[4] and spmv.hot_x_info(dAj)["table_columns"] > 0
     # another matrix of the same shape in the SAME buffers: dropping the flag once is enough
     lens = np.diff(Ap).astype(np.int64)
     np.random.default_rng(3).shuffle(lens)                                   # same n_rows, same nnz
@@ -702,8 +714,11 @@ def test_hot_x_plan_is_bit_identical(dtype, off, fill, table):
     thr = by_count[info["hot_columns"] - 1]
     assert abs(info["hot_share"] - cnt[cnt >= thr].sum() / Aj.size) < 1e-12
     if table:
-        thr = by_count[info["table_columns"] - 1]
-        assert abs(info["table_share"] - cnt[cnt >= thr].sum() / Aj.size) < 1e-12
+        # filled to capacity: whole count buckets (8 per octave) from the top, then part of the next
+        # one in column order -- so not exactly the 1000 most frequent columns, but close to them
+        assert info["table_columns"] == 1000
+        top = by_count[:1000].sum() / Aj.size
+        assert 0.85 * top <= info["table_share"] <= top + 1e-12
 
 
 def test_table_plan_for_a_short_x_under_the_static_pattern_flag():
