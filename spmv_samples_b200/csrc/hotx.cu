@@ -14,6 +14,10 @@
 // kernel x_hot[r] = x[hot_cols[r]] and the tile kernel picks its gather base by the sign of the
 // index.  Products and their order are unchanged, so y is bit-identical to the plain kernel's.
 // The CSR arrays the caller passed are not modified; the plan costs nnz * 4 bytes of HBM.
+// Ranks 0 .. K_table-1 are the plan's most frequent columns (whole count buckets from the top,
+// then part of the next one, to the capacity asked for): the persistent tile kernel
+// (merge.cu, merge_tile_table_kernel) keeps their x values in shared memory.  For an x that the L2
+// holds anyway the plan is only that: every hot column is a table column.
 // Nothing like it in the reference: its merge kernel gathers x[Aj[k]] as is
 // (merge_based/agent_spmv_orig.cuh:474-506).
 #include <cub/device/device_scan.cuh>

@@ -747,19 +747,16 @@ merge_tile_hot_kernel(MERGE_REG_KERNEL_ARGS, const ValT *__restrict__ x_hot_bias
 // Why: ncu puts the flag-form kernel on R-MAT scale 24 at 86 % of l1tex__m_l1tex2xbar_req_cycles --
 // one request per cycle per SM from the L1 to the L2 is the wall every CSR kernel here runs into
 // (~270 G gathers/s on the chip, tools/l2_gather_probe.cu), and only 7 % of the gathers hit the
-// L1.  A gather served from shared memory never becomes such a request.  On R-MAT the 13 K most
-// frequent columns of scale 24 take 28 % of the gathers, the 3.3 K of scale 27 8 %.
+// L1.  A gather served from shared memory never becomes such a request.
 // Measured (tools/table_sweep.py, L2 flushed, y bit-identical in every row):
-//   scale 24 (x 64 MB, table-only plan): 1095 us plain -> 1105 persistent without a table -> 1045
-//     with the 13 K table; request cycles 86 -> 73 %, the kernel is then short of warps (8 per
-//     scheduler at 56 registers; two or three smaller CTAs per SM, each with its own table, were
-//     slower: 1070 / 1175 / 1367 us);
-//   scale 27 (hot-x plan + table): 11.27 ms -> 10.89 persistent -> 10.34 with the 3.3 K table.
-// The table takes its space from the L1, which is what holds the gathers in flight: 99 KB of
-// shared memory (tiles + 58 KB of table) is the best size on both; at scale 24 a 154 KB table with
-// 40 % of the gathers is slower than none (1117 us), at scale 27 the 83 KB table with 19 % gives
-// 10.99 ms.  Hence option "hot_x_table_bytes".  The tile body is the flag form's, with group-local
-// barriers; products and their order are unchanged.
+//   scale 24 (x 64 MB, all-table plan): 1100 us plain -> 1105 persistent without a table -> 1000
+//     with 31 K columns (36 % of the gathers) in the table; with 13 K columns request cycles go
+//     from 86 to 73 % and the kernel is then short of warps (8 per scheduler at 56 registers; two
+//     or three smaller CTAs per SM, each with its own table, were slower: 1070 / 1175 / 1367 us);
+//   scale 27 (hot-x plan + table): 11.4 ms -> 10.9 persistent -> 10.4 with 15 K columns (15 %).
+// The table takes its space from the L1, which is what holds the gathers in flight; the sizes
+// are chosen in launch_merge ("hot_x_table_bytes").  The tile body is the flag form's, with
+// group-local barriers; products and their order are unchanged.
 #ifndef SPMV_TABLE_GROUPS
 #define SPMV_TABLE_GROUPS 8
 #endif
@@ -1180,12 +1177,18 @@ int launch_merge(const SpmvProblem<OffT, ValT> &p) {
         const int64_t tbl_opt = option_get("hot_x_table", -1);
         const bool tbl_ok = RB == kTableBlock && (tbl_opt > 0 || (tbl_opt < 0 && sizeof(ValT) == 4 && flags_form));
         constexpr int64_t tile_smem = (int64_t)sizeof(TileSmem<kTableBlock, ValT>) * kTableGroups;
-        // the option is per SM; every CTA has 1 KB reserved by the system inside a carveout size
-        int64_t tbl_bytes = option_get("hot_x_table_bytes", 99 << 10);
+        // The option is per SM (every CTA has 1 KB reserved by the system inside a carveout size);
+        // -1 = by the size of x.  What the table takes, the L1 loses, in the carveout's steps
+        // (100 / 132 / 164 / 196 KB): while x sits in the L2 (R-MAT scale 24) 163 KB is the best size
+        // and the next step a cliff (1100 us plain, 1035 / 1011 / 1000 / 1134 us at 99 / 131 / 163 /
+        // 179 KB); with x in DRAM (scale 27) the misses in flight need the L1 more than the gathers
+        // need the table (11.4 ms plain, 10.3 / 10.4 / 11.0 ms at 83 / 99 / 115 KB).
+        const bool big_x = (int64_t)p.n_cols * (int64_t)sizeof(ValT) > option_get("hot_x_min_bytes", 256ll << 20);
+        int64_t tbl_bytes = option_get("hot_x_table_bytes", -1);
+        if (tbl_bytes < 0) tbl_bytes = big_x ? 99 << 10 : 163 << 10;
         if (tbl_bytes > 226 << 10) tbl_bytes = 226 << 10;
         tbl_bytes = (tbl_bytes + 1024) / kTableCtas - 1024;
         const int64_t k_table = tbl_ok && tbl_bytes > tile_smem ? (tbl_bytes - tile_smem) / (int64_t)sizeof(ValT) : 0;
-        const bool big_x = (int64_t)p.n_cols * (int64_t)sizeof(ValT) > option_get("hot_x_min_bytes", 256ll << 20);
         const bool want_hot = hot_opt > 0 || (hot_opt < 0 && p.reuse_partition && (big_x || k_table > 0));
         const int64_t k_max = (hot_opt > 0 || big_x) ? option_get("hot_x_max_bytes", 32 << 20) / (int64_t)sizeof(ValT)
                                                      : k_table;

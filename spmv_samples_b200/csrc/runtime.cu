@@ -61,7 +61,7 @@ std::map<std::string, int64_t> &options() {
         {"hot_x_table", -1},     // shared-memory table of the most frequent columns (persistent merge tile kernel):
                                  // -1 = fp32 flag form, 0 = never, 1 = always
         {"hot_x_table_limit", -1},  // experiments: use at most this many table entries (0: persistent kernel, no table)
-        {"hot_x_table_bytes", 99 << 10},  // dynamic shared memory of that kernel (8 tiles in flight + table)
+        {"hot_x_table_bytes", -1},  // dynamic shared memory of that kernel (8 tiles in flight + table); -1 = by the size of x
         {"assume_static_pattern", 0},  // 1: every call is treated as carrying SPMVB200_FLAG_STATIC_PATTERN
         {"side_stream", 0},      // 1: small kernels a big one depends on (partition, x_hot refill) run on a side
                                  // stream forked / joined with events (measured: no gain outside the profiler)

@@ -699,7 +699,7 @@ def test_hot_x_plan_is_bit_identical(dtype, off, fill, table):
         spmv.set_option("hot_x_max_bytes", 32 << 20)
         spmv.set_option("hot_x_fill", 0)
         spmv.set_option("hot_x_table", -1)
-        spmv.set_option("hot_x_table_bytes", 99 << 10)
+        spmv.set_option("hot_x_table_bytes", -1)
         spmv.set_option("merge_algo", -1)
         spmv.release_cache()
     assert 0 < info["hot_columns"] <= 4096 and 0.25 <= info["hot_share"] <= 1.0

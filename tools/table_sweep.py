@@ -58,6 +58,6 @@ for cfg in a.configs.split(","):
               f"{100*hx['hot_share']:.1f}%  table {hx['table_columns']} cols {100*hx['table_share']:.1f}%{same}", flush=True)
     spmv.release_cache()
     spmv.set_option("hot_x_table", -1)
-    spmv.set_option("hot_x_table_bytes", 99 << 10)
+    spmv.set_option("hot_x_table_bytes", -1)
     del m, x, y, y_ref
     torch.cuda.empty_cache()
