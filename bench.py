@@ -746,6 +746,27 @@ def own_arm(args, rank, world, local_rank):
                       f"bytes are totals over the ranks; {ns} steps in flight"}
         hs.close()
 
+    if e2e is not None:
+        # what the host link alone takes for a step's copies (same pinned buffers, upload and
+        # download at once on two streams, no kernel): the floor under e2e's ms_per_step on this box
+        dx = torch.empty_like(xs[0], device="cuda")
+        dy = torch.empty_like(ys[0], device="cuda")
+        s_up, s_down = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def copies(rounds=6):
+            for _ in range(rounds):
+                with torch.cuda.stream(s_up):
+                    dx.copy_(xs[0], non_blocking=True)
+                with torch.cuda.stream(s_down):
+                    ys[0].copy_(dy, non_blocking=True)
+            s_up.synchronize()
+            s_down.synchronize()
+        copies(2)
+        e2e["host_link_floor_ms_per_step"] = timed(copies) / 6 * 1e3
+        e2e["host_link_note"] = ("a step's upload and download alone, both directions at once, from the same "
+                                 "pinned buffers (max over ranks): what this box's host link allows")
+        del dx, dy
+
     exchange_used, exchange_note = it.exchange, getattr(it, "exchange_note", "")
     offset_bits = local.Ap.element_size() * 8
     value_dtype = "f32" if local.Ax.dtype == torch.float32 else "f64"
