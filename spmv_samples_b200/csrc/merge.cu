@@ -1175,7 +1175,14 @@ int launch_merge(const SpmvProblem<OffT, ValT> &p) {
         // 1 = on; "hot_x_table_bytes" = the kernel's dynamic shared memory, tiles and table).
         const int64_t hot_opt = option_get("hot_x", -1);
         const int64_t tbl_opt = option_get("hot_x_table", -1);
-        const bool tbl_ok = RB == kTableBlock && (tbl_opt > 0 || (tbl_opt < 0 && sizeof(ValT) == 4 && flags_form));
+        // by default only where the persistent grid has work for every SM: at least four rounds of
+        // tiles per group (4.8 M path items on 148 SMs); a smaller matrix is spread over more SMs by
+        // one CTA per tile
+        const DeviceInfo *tdi = nullptr;
+        SPMV_TRY(current_device_info(&tdi));
+        const bool tbl_ok = RB == kTableBlock &&
+                            (tbl_opt > 0 || (tbl_opt < 0 && sizeof(ValT) == 4 && flags_form &&
+                                             num_tiles >= (int64_t)tdi->sm_count * kTableGroups * 4));
         constexpr int64_t tile_smem = (int64_t)sizeof(TileSmem<kTableBlock, ValT>) * kTableGroups;
         // The option is per SM (every CTA has 1 KB reserved by the system inside a carveout size);
         // -1 = by the size of x.  What the table takes, the L1 loses, in the carveout's steps
@@ -1213,8 +1220,7 @@ int launch_merge(const SpmvProblem<OffT, ValT> &p) {
                 const uint32_t table_n = (uint32_t)tn;
                 const size_t smem = (size_t)tile_smem + (size_t)table_n * sizeof(ValT);
                 SPMV_TRY(apply_max_dynamic_smem(reinterpret_cast<const void *>(tkernel), (int64_t)smem));
-                const DeviceInfo *di = nullptr;
-                SPMV_TRY(current_device_info(&di));
+                const DeviceInfo *di = tdi;
                 const int64_t want_ctas = (num_tiles + kTableGroups - 1) / kTableGroups;
                 const int64_t max_ctas = (int64_t)di->sm_count * kTableCtas;
                 make_launch_cfg(lc, dim3((unsigned)(want_ctas < max_ctas ? want_ctas : max_ctas)),

@@ -135,6 +135,9 @@ def _rank_main(rank, world, port, exchange, out_dir, rebalance=False):
     np.save(os.path.join(out_dir, f"x_{exchange}_{rank}.npy"), it.current_x().cpu().numpy())
     open(os.path.join(out_dir, f"ex_{exchange}_{rank}.txt"), "w").write(
         it.exchange + " " + ",".join(map(str, it.shard.row_bounds)))
+    from spmv_samples_b200 import spmv
+    open(os.path.join(out_dir, f"tbl_{exchange}_{rank}.txt"), "w").write(
+        str(spmv.hot_x_info(it.shard.csr.Aj)["table_columns"]))
     it.close()
     dist.destroy_process_group()
 
@@ -153,6 +156,33 @@ def test_two_gpu_sharded_iteration_matches_single_gpu(tmp_path, exchange):
     used, bounds = open(tmp_path / f"ex_{exchange}_0.txt").read().split(" ")
     Ap, _, _ = g.rmat(14, 16, 7, offset_dtype=np.int64)
     assert bounds == ",".join(map(str, cpu.row_split(Ap, 2).tolist()))     # bit-exact split
+    m = gen.rmat(14, 16, 7, offset=torch.int64)
+    it = PowerIteration(shard_rows(m, 0, 1), m.n_rows, kind="auto")
+    for _ in range(6):
+        it.step()
+    ref = it.current_x().cpu().numpy()
+    it.close()
+    assert np.linalg.norm(x0.astype(np.float64) - ref) <= 1e-5 * np.linalg.norm(ref)
+
+
+@pytest.mark.parametrize("exchange", ["mc", "p2p"])
+def test_two_gpu_table_kernel_feeds_the_exchange(tmp_path, exchange, monkeypatch):
+    """The persistent table form of the merge tile kernel (forced through SPMVB200_OPTS in the rank
+    processes: these shards are far too small for it by default) with the fused exchange -- peer
+    stores or one multimem.st per row: the replicas agree bit for bit and the iteration is the
+    single-GPU one."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    from spmv_samples_b200 import generate as gen
+    from spmv_samples_b200.dist import PowerIteration, shard_rows
+    monkeypatch.setenv("SPMVB200_OPTS", "hot_x_table=1")
+    mp.spawn(_rank_main, args=(2, _free_port(), exchange, str(tmp_path)), nprocs=2, join=True)
+    monkeypatch.delenv("SPMVB200_OPTS")
+    x0 = np.load(tmp_path / f"x_{exchange}_0.npy")
+    x1 = np.load(tmp_path / f"x_{exchange}_1.npy")
+    assert np.array_equal(x0, x1)
+    assert all(int(open(tmp_path / f"tbl_{exchange}_{r}.txt").read()) > 0 for r in range(2))
     m = gen.rmat(14, 16, 7, offset=torch.int64)
     it = PowerIteration(shard_rows(m, 0, 1), m.n_rows, kind="auto")
     for _ in range(6):

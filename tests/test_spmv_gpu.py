@@ -552,23 +552,31 @@ def test_static_pattern_flag_reuses_and_never_goes_stale():
         spmv.set_option("hot_x", -1)
     assert torch.equal(y0, y1)
     assert launches[1] == launches[0] - 1 and launches[2] == launches[1]     # the search is skipped
-    # default options: the flagged calls build the table plan once (more launches), then refill + tile + fixup
-    for flag in (True, True):
-        before = spmv.launch_count()
-        spmv.spmv_ex("merge", dAp, dAj, dAx, dx, y1, static_pattern=flag)
-        launches.append(spmv.launch_count() - before)
-    torch.cuda.synchronize()
-    assert torch.equal(y0, y1)
-    assert launches[3] > launches[4] and spmv.hot_x_info(dAj)["table_columns"] > 0
-    # another matrix of the same shape in the SAME buffers: dropping the flag once is enough
-    lens = np.diff(Ap).astype(np.int64)
-    np.random.default_rng(3).shuffle(lens)                                   # same n_rows, same nnz
-    Ap3 = np.zeros(n + 1, dtype=Ap.dtype)
-    np.cumsum(lens, out=Ap3[1:])
-    dAp.copy_(torch.from_numpy(Ap3).cuda())
-    spmv.spmv_ex("merge", dAp, dAj, dAx, dx, y0, static_pattern=False)
-    spmv.spmv_ex("merge", dAp, dAj, dAx, dx, y1, static_pattern=True)
-    torch.cuda.synchronize()
+    # with the table plan (forced: the matrix is far too small for it by default): the flagged calls
+    # build it once (more launches), then refill + tile + fixup
+    spmv.set_option("hot_x_table", 1)
+    try:
+        for flag in (True, True):
+            before = spmv.launch_count()
+            spmv.spmv_ex("merge", dAp, dAj, dAx, dx, y1, static_pattern=flag)
+            launches.append(spmv.launch_count() - before)
+        torch.cuda.synchronize()
+        assert torch.equal(y0, y1)
+        assert launches[3] > launches[4] and spmv.hot_x_info(dAj)["table_columns"] > 0
+        # another matrix of the same shape in the SAME buffers: dropping the flag once is enough
+        # (the search runs again, the plan left at this address is dropped and rebuilt)
+        lens = np.diff(Ap).astype(np.int64)
+        np.random.default_rng(3).shuffle(lens)                                   # same n_rows, same nnz
+        Ap3 = np.zeros(n + 1, dtype=Ap.dtype)
+        np.cumsum(lens, out=Ap3[1:])
+        dAp.copy_(torch.from_numpy(Ap3).cuda())
+        spmv.spmv_ex("merge", dAp, dAj, dAx, dx, y0, static_pattern=False)
+        assert spmv.hot_x_info(dAj)["hot_columns"] == 0
+        spmv.spmv_ex("merge", dAp, dAj, dAx, dx, y1, static_pattern=True)
+        torch.cuda.synchronize()
+    finally:
+        spmv.set_option("hot_x_table", -1)
+        spmv.release_cache()
     assert torch.equal(y0, y1)
     assert_within_tolerance(y1.cpu().numpy(), Ap3, Aj, Ax, x, "static pattern after in-place change")
     a = _lib.Args()
@@ -726,8 +734,8 @@ def test_table_plan_for_a_short_x_under_the_static_pattern_flag():
     table-only plan (every hot column is a table column) from its first flagged call on, an
     unflagged call drops it again; y stays bit-identical throughout."""
     from spmv_samples_b200 import spmv
-    Ap, Aj, Ax = g.rmat(16, 16, 33)
-    n = 1 << 16
+    Ap, Aj, Ax = g.rmat(19, 16, 33)   # 8.9 M path items: enough tiles for the persistent grid
+    n = 1 << 19
     x = g.gen_x(9, n)
     dAp, dAj, dAx, dx = dev(Ap), dev(Aj), dev(Ax), dev(x)
     ys = []
