@@ -747,8 +747,8 @@ def own_arm(args, rank, world, local_rank):
         hs.close()
 
     if e2e is not None:
-        # what the host link alone takes for a step's copies (same pinned buffers, upload and
-        # download at once on two streams, no kernel): the floor under e2e's ms_per_step on this box
+        # what the host link takes for a step's copies alone (same pinned buffers, upload and
+        # download at once on two streams, no kernel): e2e's ms_per_step cannot be far below it
         dx = torch.empty_like(xs[0], device="cuda")
         dy = torch.empty_like(ys[0], device="cuda")
         s_up, s_down = torch.cuda.Stream(), torch.cuda.Stream()
@@ -762,9 +762,9 @@ def own_arm(args, rank, world, local_rank):
             s_up.synchronize()
             s_down.synchronize()
         copies(2)
-        e2e["host_link_floor_ms_per_step"] = timed(copies) / 6 * 1e3
-        e2e["host_link_note"] = ("a step's upload and download alone, both directions at once, from the same "
-                                 "pinned buffers (max over ranks): what this box's host link allows")
+        e2e["host_copies_alone_ms_per_step"] = timed(copies) / 6 * 1e3
+        e2e["host_copies_note"] = ("a step's upload and download alone, both directions at once, from the same "
+                                   "pinned buffers, no kernel (max over ranks): what this box's host link takes")
         del dx, dy
 
     exchange_used, exchange_note = it.exchange, getattr(it, "exchange_note", "")

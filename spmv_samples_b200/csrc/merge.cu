@@ -1166,8 +1166,7 @@ int launch_merge(const SpmvProblem<OffT, ValT> &p) {
         const bool occ = sizeof(ValT) == 4 && (sizeof(OffT) == 4 || !flags_form);
         // multicast peers (one pointer): its own fp32 flag-form variant, 8 CTAs per SM
         const bool mc_f32 = p.peers.n < 0 && sizeof(ValT) == 4 && flags_form;
-        // hot-x plan (hotx.cu): by default only for a caller that vouches for an unchanged matrix
-        // and an x far longer than the TLB and the L2 reach
+        // hot-x plan (hotx.cu): by default only for a caller that vouches for an unchanged matrix.
         // Two uses of it.  (a) x far longer than the TLB and the L2 reach ("hot_x_min_bytes"): up to
         // "hot_x_max_bytes" of the most frequent columns' x in one dense array.  (b) whatever the
         // size of x: the few thousand most frequent columns in a shared-memory table of the
