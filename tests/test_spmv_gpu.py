@@ -729,6 +729,41 @@ def test_hot_x_plan_is_bit_identical(dtype, off, fill, table):
         assert 0.85 * top <= info["table_share"] <= top + 1e-12
 
 
+@pytest.mark.parametrize("off", [np.int32, np.int64])
+def test_table_kernel_repeats_bit_for_bit(off):
+    """The persistent table kernel runs 8 tiles per CTA behind group-local barriers and reuses each
+    group's shared memory from tile to tile without a barrier in between: 40 launches on a matrix of
+    a few thousand tiles (hub rows spanning many of them) must give the plain kernel's bits every
+    time."""
+    from spmv_samples_b200 import spmv
+    Ap, Aj, Ax = g.rmat(17, 16, 77, offset_dtype=off)
+    n = 1 << 17
+    dAp, dAj, dAx = dev(Ap), dev(Aj), dev(Ax)
+    xs = [dev(g.gen_x(100 + i, n)) for i in range(4)]
+    ref = []
+    spmv.release_cache()
+    spmv.set_option("hot_x", 0)
+    for dx in xs:
+        y = torch.full((n,), float("nan"), device="cuda")
+        spmv.SpMV("merge", n, n, Aj.size, dAp, dAj, dAx, dx, y)
+        ref.append(y)
+    spmv.set_option("hot_x", 1)
+    spmv.set_option("hot_x_table", 1)
+    bad = 0
+    try:
+        for rep in range(40):
+            y = torch.full((n,), float("nan"), device="cuda")
+            spmv.SpMV("merge", n, n, Aj.size, dAp, dAj, dAx, xs[rep % 4], y)
+            bad += int(not torch.equal(y, ref[rep % 4]))
+        torch.cuda.synchronize()
+        assert spmv.hot_x_info(dAj)["table_columns"] > 0
+    finally:
+        spmv.set_option("hot_x", -1)
+        spmv.set_option("hot_x_table", -1)
+        spmv.release_cache()
+    assert bad == 0
+
+
 def test_table_plan_for_a_short_x_under_the_static_pattern_flag():
     """Default options, x far below "hot_x_min_bytes": a caller that vouches for the pattern gets the
     table-only plan (every hot column is a table column) from its first flagged call on, an
