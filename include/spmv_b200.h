@@ -251,7 +251,7 @@ SPMVB200_API int spmvb200_gather_yardstick(int64_t x_elements, int64_t gathers, 
  * array x_hot (refilled from x before every SpMV).  Products and their order are unchanged: y is
  * bit-identical.  Costs nnz * 4 bytes of device memory, built at the first flagged call.  Reports
  * what was built for this Aj on the current device (0 columns = no plan).  The flag therefore
- * vouches for Aj as well as Ap.  Callers behind the reference's SpMV(kind_str, ...) signature,
+ * vouches for Aj as well as Ap.  If the device has no room for the plan, the calls proceed without it.  Callers behind the reference's SpMV(kind_str, ...) signature,
  * which has no flags, vouch through option "assume_static_pattern" = 1 (main.cu does for its
  * timing loop).  Nothing in the reference corresponds (it gathers x[Aj[k]] as is,
  * merge_based/agent_spmv_orig.cuh:474-506). */

@@ -218,6 +218,16 @@ int build(const int32_t *Aj, int64_t nnz, int32_t n_cols, int64_t k_max, int64_t
             record_cuda_error(_e, #expr, __FILE__, __LINE__);           \
             cleanup();                                                  \
             entry_free(e);                                              \
+            if (_e == cudaErrorMemoryAllocation) {                      \
+                /* no room for the plan (nnz * 4 bytes and its scratch): the SpMV does without */ \
+                (void)cudaGetLastError();                               \
+                e.nnz = nnz;                                            \
+                e.n_cols = n_cols;                                      \
+                e.k_max = k_max;                                        \
+                e.k_table = k_table;                                    \
+                e.none = true;                                          \
+                return SPMVB200_OK;                                     \
+            }                                                           \
             return SPMVB200_ERR_CUDA;                                   \
         }                                                               \
     } while (0)
