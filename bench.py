@@ -60,8 +60,9 @@ def parse_args():
                    help="multi-GPU: rounds of re-splitting the rows from measured per-rank local "
                         "step times (partition + tile kernel + fix-up + norm) before the timed region")
     p.add_argument("--e2e-steps", type=int, default=24)
-    p.add_argument("--e2e-slots", type=int, default=3, choices=[1, 2, 3, 4],
-                   help="host-buffer calls in flight in the e2e leg (own stream + device x/y each)")
+    p.add_argument("--e2e-slots", type=int, default=0, choices=[0, 1, 2, 3, 4],
+                   help="host-buffer calls in flight in the e2e leg (own stream + device x/y each); "
+                        "0 = 4 on one GPU (measured: 20.6 / 12.5 / 12.0 ms per step with 2 / 3 / 4), 3 on several")
     p.add_argument("--cpu-seconds", type=float, default=15.0,
                    help="budget of the cpu_baseline leg (own arm)")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -690,7 +691,7 @@ def own_arm(args, rank, world, local_rank):
             dist.all_reduce(td, op=dist.ReduceOp.MAX)
         return float(td.item())
 
-    k, ns = args.e2e_steps, args.e2e_slots
+    k, ns = args.e2e_steps, args.e2e_slots or (4 if world == 1 else 3)
     if k > 0 and world == 1:
         mat = CsrMatrix.from_device(local)
         xs = [torch.empty(n_cols, dtype=local.Ax.dtype, pin_memory=True) for _ in range(ns)]

@@ -85,7 +85,7 @@ class CsrMatrix:
     def wait(self, slot: int) -> None:
         _lib.check(_lib.lib().spmvb200_matrix_wait(self._h, int(slot)), "spmvb200_matrix_wait")
 
-    def spmv_many(self, xs, ys, kind: str = "auto", slots: int = 3) -> None:
+    def spmv_many(self, xs, ys, kind: str = "auto", slots: int = MAX_SLOTS) -> None:
         """ys[i] = A @ xs[i] for a sequence of independent right-hand sides, `slots` in flight
         (3: one uploading, one in the kernel, one downloading)."""
         if not 1 <= slots <= MAX_SLOTS:
