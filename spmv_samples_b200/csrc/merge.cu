@@ -770,7 +770,7 @@ template <int HAS_PEERS, typename OffT, typename ValT>
 __global__ void __launch_bounds__(kTableGroups *kTableBlock, kTableCtas)
 merge_tile_table_kernel(MERGE_REG_KERNEL_ARGS, const ValT *__restrict__ x_hot_biased,
                         const ValT *__restrict__ x_hot, uint32_t table_n, int64_t num_tiles) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     using Smem = TileSmem<kTableBlock, ValT>;
     Smem *const groups = reinterpret_cast<Smem *>(smem_raw);
     ValT *const table = reinterpret_cast<ValT *>(smem_raw + sizeof(Smem) * kTableGroups);
